@@ -1,0 +1,745 @@
+// extern "C" boundary of libsla_b200 (declared in include/sla_b200.h): composes the batched kernels
+// (DMMA GEMM with fused diagonal scaling, LDR factorisation, LU/inverse with log|det| and sign,
+// element-wise helpers) into the reference's operations.  Every composition cites the reference lines
+// it reproduces; scratch use follows the reference's M / M' / M'' roles where that matters for the
+// documented aliasing rules.
+#include <new>
+
+#include "../../include/sla_b200.h"
+#include "sla_kernels.h"
+
+using namespace sla;
+
+struct sla_handle_s {
+    cudaStream_t stream;
+};
+
+namespace {
+
+#define CK(expr)                                            \
+    do {                                                    \
+        cudaError_t e__ = (expr);                           \
+        if (e__ != cudaSuccess) return 1000 + (int)e__;     \
+    } while (0)
+#define CKI(expr)                 \
+    do {                          \
+        int r__ = (expr);         \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+constexpr int NSCAL = 8;  // per-matrix scalar slots in a workspace
+
+// Workspace blob = LDRWorkspace (src/LDR.jl:51-70): M, M', M'' plus the LU/QR scratch and scalars.
+template <typename T> struct Ws {
+    T *M, *Mp, *Mpp, *X, *Tw;
+    double* sc;  // NSCAL * batch
+    T* st;       // NSCAL * batch
+    int* info;   // batch
+    size_t tw_elems;
+    static size_t bytes(int n, int batch) {
+        size_t nn = (size_t)n * n * batch * sizeof(T);
+        size_t b = 4 * align_up(nn);
+        b += align_up(ldr_twork_elems<T>(n) * (size_t)batch * sizeof(T));
+        b += align_up((size_t)NSCAL * batch * sizeof(double));
+        b += align_up((size_t)NSCAL * batch * sizeof(T));
+        b += align_up((size_t)batch * sizeof(int));
+        return b;
+    }
+    Ws(void* blob, int n, int batch) {
+        char* p = static_cast<char*>(blob);
+        size_t nn = align_up((size_t)n * n * batch * sizeof(T));
+        M = (T*)p; p += nn;
+        Mp = (T*)p; p += nn;
+        Mpp = (T*)p; p += nn;
+        X = (T*)p; p += nn;
+        tw_elems = ldr_twork_elems<T>(n);
+        Tw = (T*)p; p += align_up(tw_elems * (size_t)batch * sizeof(T));
+        sc = (double*)p; p += align_up((size_t)NSCAL * batch * sizeof(double));
+        st = (T*)p; p += align_up((size_t)NSCAL * batch * sizeof(T));
+        info = (int*)p;
+    }
+};
+
+template <typename T> struct Ctx {
+    cudaStream_t s;
+    int n, batch;
+    long long nn;  // n*n
+    Ws<T> w;
+    Ctx(sla_handle_t h, int n_, int batch_, void* ws) : s(h->stream), n(n_), batch(batch_), nn((long long)n_ * n_), w(ws, n_, batch_) {}
+
+    int copy(T* dst, const T* src) const {
+        if (dst == src) return 0;
+        CK(cudaMemcpyAsync(dst, src, (size_t)nn * batch * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+    int copy_d(double* dst, const double* src) const {
+        if (dst == src) return 0;
+        CK(cudaMemcpyAsync(dst, src, (size_t)n * batch * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        return 0;
+    }
+    // C = rowscale * (op(A) op(B)) * colscale  (+ C)
+    int gemm(T* C, int opa, const T* A, long long sA, int opb, const T* B, long long sB, const double* rs = nullptr,
+             int rs_mode = SCALE_NONE, const double* cs = nullptr, int cs_mode = SCALE_NONE, int accumulate = 0,
+             long long sC = -1) const {
+        GemmArgs<T> g{};
+        g.A = A; g.B = B; g.C = C;
+        g.strideA = sA; g.strideB = sB; g.strideC = (sC < 0) ? nn : sC;
+        g.lda = g.ldb = g.ldc = n;
+        g.M = g.N = g.K = n;
+        g.rs = rs; g.stride_rs = n; g.rs_mode = rs_mode; g.rs_div = 0; g.stride_rs_hi = 0;
+        g.cs = cs; g.stride_cs = n; g.cs_mode = cs_mode;
+        g.accumulate = accumulate;
+        g.batch = batch;
+        CK(gemm_batched<T>(opa, opb, g, s));
+        return 0;
+    }
+    // ldr! on buffer Lbuf (optionally reading its input from Ain): Q -> Lbuf, d, R0 -> Rout
+    int ldr(T* Lbuf, double* d, T* Rout, const T* Ain = nullptr, long long sAin = 0) const {
+        LdrArgs<T> a{};
+        a.L = Lbuf; a.strideL = nn; a.ldl = n;
+        a.Ain = Ain; a.strideAin = sAin; a.ldain = n;
+        a.d = d; a.stride_d = n;
+        a.R = Rout; a.strideR = nn; a.ldr = n;
+        a.Twork = w.Tw; a.strideT = (long long)w.tw_elems;
+        a.jpvt_out = nullptr;
+        a.n = n; a.batch = batch;
+        CK(ldr_batched<T>(a, s));
+        return 0;
+    }
+    // LU of A (destroyed).  invert: A^-1 -> X (and back into A if copy_back)
+    int lu(T* A, T* X, int invert, int copy_back, double* logdet, T* sign) const {
+        LuArgs<T> a{};
+        a.A = A; a.strideA = nn; a.lda = n;
+        a.X = X; a.strideX = nn; a.ldx = n;
+        a.logdet = logdet; a.sign = sign;
+        a.ipiv_out = nullptr; a.info = w.info;
+        a.invert = invert; a.copy_back = copy_back;
+        a.n = n; a.batch = batch;
+        CK(lu_batched<T>(a, s));
+        return 0;
+    }
+    int scale(T* dst, const T* src, int op, const double* rs, int rs_mode, const double* cs, int cs_mode) const {
+        CK(scale_batched<T>(dst, nn, n, src, nn, n, op, rs, n, rs_mode, cs, n, cs_mode, n, batch, s));
+        return 0;
+    }
+    int logsum(double* out, const double* d, int mode) const {
+        CK(logsum_batched(out, d, n, mode, n, batch, s));
+        return 0;
+    }
+    double* sc(int k) const { return w.sc + (size_t)k * batch; }
+    T* st(int k) const { return w.st + (size_t)k * batch; }
+};
+
+// ---------------------------------------------------------------------------------------------
+template <typename T> int ldr_impl(sla_handle_t h, int n, int batch, T* L, double* d, T* R, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    return c.ldr(L, d, R);
+}
+
+template <typename T>
+int ldr_from_impl(sla_handle_t h, int n, int batch, const T* A, long long sA, T* L, double* d, T* R, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    return c.ldr(L, d, R, A, sA);
+}
+
+template <typename T> int set_identity_impl(sla_handle_t h, int n, int batch, T* L, double* d, T* R) {
+    CK(set_identity_batched<T>(L, (long long)n * n, n, n, batch, h->stream));
+    CK(fill_batched(d, 1.0, (long long)n * batch, h->stream));
+    CK(set_identity_batched<T>(R, (long long)n * n, n, n, batch, h->stream));
+    return 0;
+}
+
+// copyto!(A, F, ws): overloaded_functions.jl:34-45
+template <typename T>
+int ldr_to_mat_impl(sla_handle_t h, int n, int batch, T* A, const T* L, const double* d, const T* R, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.scale(c.w.M, R, OP_N, d, SCALE_MUL, nullptr, SCALE_NONE));  // M = D R      (:39-41)
+    return c.gemm(A, OP_N, L, c.nn, OP_N, c.w.M, c.nn);               // A = L M      (:42)
+}
+
+// adjoint!(At, F, ws): overloaded_functions.jl:75-86
+template <typename T>
+int adjoint_impl(sla_handle_t h, int n, int batch, T* At, const T* L, const double* d, const T* R, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.scale(c.w.M, L, OP_C, d, SCALE_MUL, nullptr, SCALE_NONE));  // M = D L^H    (:80-83)
+    return c.gemm(At, OP_C, R, c.nn, OP_N, c.w.M, c.nn);              // At = R^H M   (:84)
+}
+
+// lmul!(U::Matrix, V::LDR): overloaded_functions.jl:126-145
+template <typename T>
+int lmul_mat_ldr_impl(sla_handle_t h, int n, int batch, const T* U, long long sU, T* L, double* d, T* R, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.gemm(c.w.M, OP_N, U, sU, OP_N, L, c.nn, nullptr, SCALE_NONE, d, SCALE_MUL));  // (U Lv) Dv   (:133-135)
+    CKI(c.ldr(L, d, c.w.Mp, c.w.M, c.nn));                                               // ldr!        (:138), R0 -> M'
+    CKI(c.gemm(c.w.Mpp, OP_N, c.w.Mp, c.nn, OP_N, R, c.nn));                             // R0 Rv       (:141)
+    return c.copy(R, c.w.Mpp);                                                           //             (:142)
+}
+
+// rmul!(U::LDR, V::Matrix): overloaded_functions.jl:234-253
+template <typename T>
+int rmul_ldr_mat_impl(sla_handle_t h, int n, int batch, T* L, double* d, T* R, const T* V, long long sV, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.gemm(c.w.M, OP_N, R, c.nn, OP_N, V, sV, d, SCALE_MUL));  // Du (Ru V)      (:241-243)
+    CKI(c.ldr(c.w.M, d, R));                                        // ldr!           (:246): L0 in M, R0 -> U.R
+    CKI(c.gemm(c.w.Mp, OP_N, L, c.nn, OP_N, c.w.M, c.nn));          // Lu L0          (:249)
+    return c.copy(L, c.w.Mp);                                       //                (:250)
+}
+
+// lmul!(U::LDR, V::LDR): overloaded_functions.jl:166-193
+template <typename T>
+int lmul_ldr_ldr_impl(sla_handle_t h, int n, int batch, const T* UL, const double* Ud, const T* UR, T* VL,
+                      double* Vd, T* VR, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.gemm(c.w.M, OP_N, UR, c.nn, OP_N, VL, c.nn, Ud, SCALE_MUL, Vd, SCALE_MUL));  // Du (Ru Lv) Dv  (:173-179)
+    CKI(c.ldr(c.w.M, Vd, c.w.Mp));                                                      // ldr!           (:182)
+    CKI(c.gemm(VL, OP_N, UL, c.nn, OP_N, c.w.M, c.nn));                                 // L1 = Lu L0     (:185-186)
+    CKI(c.gemm(c.w.Mpp, OP_N, c.w.Mp, c.nn, OP_N, VR, c.nn));                           // R1 = R0 Rv     (:189)
+    return c.copy(VR, c.w.Mpp);                                                         //                (:190)
+}
+
+// rmul!(U::LDR, V::LDR): overloaded_functions.jl:274-301
+template <typename T>
+int rmul_ldr_ldr_impl(sla_handle_t h, int n, int batch, T* UL, double* Ud, T* UR, const T* VL, const double* Vd,
+                      const T* VR, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.gemm(c.w.M, OP_N, UR, c.nn, OP_N, VL, c.nn, Ud, SCALE_MUL, Vd, SCALE_MUL));  // Du (Ru Lv) Dv  (:281-287)
+    CKI(c.ldr(c.w.M, Ud, c.w.Mp));                                                      // ldr!           (:290)
+    CKI(c.gemm(c.w.Mpp, OP_N, UL, c.nn, OP_N, c.w.M, c.nn));                            // L1 = Lu L0     (:293)
+    CKI(c.copy(UL, c.w.Mpp));                                                           //                (:294)
+    return c.gemm(UR, OP_N, c.w.Mp, c.nn, OP_N, VR, c.nn);                              // R1 = R0 Rv     (:297-298)
+}
+
+// lmul!(U::LDR, V::Matrix): overloaded_functions.jl:97-106
+template <typename T>
+int lmul_ldr_mat_impl(sla_handle_t h, int n, int batch, const T* L, const double* d, const T* R, T* V, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.gemm(c.w.M, OP_N, R, c.nn, OP_N, V, c.nn, d, SCALE_MUL));  // Du (Ru V)
+    return c.gemm(V, OP_N, L, c.nn, OP_N, c.w.M, c.nn);              // Lu (...)
+}
+
+// rmul!(U::Matrix, V::LDR): overloaded_functions.jl:205-214
+template <typename T>
+int rmul_mat_ldr_impl(sla_handle_t h, int n, int batch, T* U, const T* L, const double* d, const T* R, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.gemm(c.w.M, OP_N, U, c.nn, OP_N, L, c.nn, nullptr, SCALE_NONE, d, SCALE_MUL));  // (U Lv) Dv
+    return c.gemm(U, OP_N, c.w.M, c.nn, OP_N, R, c.nn);                                    // (...) Rv
+}
+
+template <typename T> int det_lu_impl(sla_handle_t h, int n, int batch, T* A, double* logdet, T* sign, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    return c.lu(A, nullptr, 0, 0, logdet, sign);
+}
+
+template <typename T> int inv_lu_impl(sla_handle_t h, int n, int batch, T* A, double* logdet, T* sign, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    return c.lu(A, c.w.X, 1, 1, logdet, sign);
+}
+
+// logabsdet(F, ws): overloaded_functions.jl:721-733
+template <typename T>
+int logabsdet_impl(sla_handle_t h, int n, int batch, const T* L, const double* d, const T* R, double* logdet,
+                   T* sign, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.copy(c.w.M, L));
+    CKI(c.lu(c.w.M, nullptr, 0, 0, c.sc(0), c.st(0)));
+    CKI(c.logsum(c.sc(1), d, SCALE_NONE));
+    CKI(c.copy(c.w.M, R));
+    CKI(c.lu(c.w.M, nullptr, 0, 0, c.sc(2), c.st(2)));
+    CombineArgs<T> a{};
+    a.lterm[0] = c.sc(0); a.lterm[1] = c.sc(1); a.lterm[2] = c.sc(2);
+    a.lcoef[0] = a.lcoef[1] = a.lcoef[2] = 1.0; a.nl = 3;
+    a.sterm[0] = c.st(0); a.sterm[1] = c.st(2); a.ns = 2;
+    a.logdet = logdet; a.sign = sign; a.batch = batch;
+    CK(combine_batched<T>(a, c.s));
+    return 0;
+}
+
+// inv_IpA!(G, A, ws): exported_functions.jl:25-71
+template <typename T>
+int inv_IpA_impl(sla_handle_t h, int n, int batch, T* G, const T* L, const double* d, const T* R, double* logdet,
+                 T* sign, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.copy(c.w.Mp, R));                                          // :32-33
+    CKI(c.lu(c.w.Mp, c.w.X, 1, 0, nullptr, c.st(0)));                // Ra^-1 -> X, sgn          (:34)
+    CK(ipa_combine_batched<T>(c.w.M, c.w.X, L, d, n, batch, c.s));   // M = La D- + Ra^-1 D+^-1  (:37-57)
+    CKI(c.logsum(c.sc(1), d, SCALE_MUL_MAX1));                       // log det D+               (:49-50)
+    CKI(c.lu(c.w.M, c.w.Mpp, 1, 0, c.sc(2), c.st(2)));               // M^-1 -> M''              (:60-61)
+    CKI(c.gemm(G, OP_N, c.w.X, c.nn, OP_N, c.w.Mpp, c.nn));          // G = Ra^-1 D+^-1 M^-1     (:64)
+    CombineArgs<T> a{};
+    a.lterm[0] = c.sc(1); a.lcoef[0] = -1.0; a.lterm[1] = c.sc(2); a.lcoef[1] = 1.0; a.nl = 2;  // :68
+    a.sterm[0] = c.st(0); a.sterm[1] = c.st(2); a.ns = 2;                                        // :67
+    a.logdet = logdet; a.sign = sign; a.batch = batch;
+    CK(combine_batched<T>(a, c.s));
+    return 0;
+}
+
+// shared prologue of inv_IpUV! / inv_UpV!: sgn det Lu, Rv^-1 Dv+^-1 -> X, Du+^-1 Lu^H -> M, log dets
+template <typename T>
+int uv_prologue(const Ctx<T>& c, const T* UL, const double* Ud, const T* VR, const double* Vd) {
+    CKI(c.copy(c.w.M, UL));                                                               // :107 / :221
+    CKI(c.lu(c.w.M, nullptr, 0, 0, nullptr, c.st(3)));                                    // sgn det Lu
+    CKI(c.copy(c.w.Mp, VR));                                                              // :111-112
+    CKI(c.lu(c.w.Mp, c.w.X, 1, 0, nullptr, c.st(0)));                                     // Rv^-1 -> X
+    CKI(c.scale(c.w.X, c.w.X, OP_N, nullptr, SCALE_NONE, Vd, SCALE_DIV_MAX1));            // Rv^-1 Dv+^-1 (:124)
+    CKI(c.logsum(c.sc(0), Vd, SCALE_MUL_MAX1));                                           // log det Dv+
+    CKI(c.logsum(c.sc(1), Ud, SCALE_MUL_MAX1));                                           // log det Du+
+    return c.scale(c.w.M, UL, OP_C, Ud, SCALE_DIV_MAX1, nullptr, SCALE_NONE);             // Du+^-1 Lu^H  (:136-137)
+}
+
+template <typename T> int uv_epilogue(const Ctx<T>& c, double* logdet, T* sign) {
+    CombineArgs<T> a{};
+    a.lterm[0] = c.sc(0); a.lcoef[0] = -1.0;   // -log det Dv+
+    a.lterm[1] = c.sc(2); a.lcoef[1] = 1.0;    // +log det M^-1
+    a.lterm[2] = c.sc(1); a.lcoef[2] = -1.0;   // -log det Du+
+    a.nl = 3;
+    a.sterm[0] = c.st(0); a.sconj[0] = 0;      // sgn det Rv^-1
+    a.sterm[1] = c.st(2); a.sconj[1] = 0;      // sgn det M^-1
+    a.sterm[2] = c.st(3); a.sconj[2] = 1;      // conj(sgn det Lu)
+    a.ns = 3;
+    a.logdet = logdet; a.sign = sign; a.batch = c.batch;
+    CK(combine_batched<T>(a, c.s));
+    return 0;
+}
+
+// inv_IpUV!(G, U, V, ws): exported_functions.jl:97-177
+template <typename T>
+int inv_IpUV_impl(sla_handle_t h, int n, int batch, T* G, const T* UL, const double* Ud, const T* UR, const T* VL,
+                  const double* Vd, const T* VR, double* logdet, T* sign, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(uv_prologue(c, UL, Ud, VR, Vd));
+    CKI(c.gemm(G, OP_N, UR, c.nn, OP_N, VL, c.nn, Ud, SCALE_MUL_MIN1, Vd, SCALE_MUL_MIN1));  // Du- (Ru Lv) Dv-  (:146-155)
+    CKI(c.gemm(G, OP_N, c.w.M, c.nn, OP_N, c.w.X, c.nn, nullptr, 0, nullptr, 0, 1));          // += M M'          (:158-162)
+    CKI(c.lu(G, c.w.Mpp, 1, 0, c.sc(2), c.st(2)));                                            // M^-1 -> M''      (:165-166)
+    CKI(c.gemm(c.w.Mp, OP_N, c.w.Mpp, c.nn, OP_N, c.w.M, c.nn));                              // M^-1 Du+^-1 Lu^H (:169)
+    CKI(c.gemm(G, OP_N, c.w.X, c.nn, OP_N, c.w.Mp, c.nn));                                    // G                (:170)
+    return uv_epilogue(c, logdet, sign);                                                      //                  (:173-174)
+}
+
+// inv_UpV!(G, U, V, ws): exported_functions.jl:211-289
+template <typename T>
+int inv_UpV_impl(sla_handle_t h, int n, int batch, T* G, const T* UL, const double* Ud, const T* UR, const T* VL,
+                 const double* Vd, const T* VR, double* logdet, T* sign, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(uv_prologue(c, UL, Ud, VR, Vd));
+    CKI(c.gemm(G, OP_N, UR, c.nn, OP_N, c.w.X, c.nn, Ud, SCALE_MUL_MIN1));                     // Du- (Ru Rv^-1 Dv+^-1) (:260-261)
+    CKI(c.gemm(G, OP_N, c.w.M, c.nn, OP_N, VL, c.nn, nullptr, 0, Vd, SCALE_MUL_MIN1, 1));      // += (Du+^-1 Lu^H Lv) Dv- (:269-274)
+    CKI(c.lu(G, c.w.Mpp, 1, 0, c.sc(2), c.st(2)));                                             // M^-1             (:277-278)
+    CKI(c.gemm(c.w.Mp, OP_N, c.w.X, c.nn, OP_N, c.w.Mpp, c.nn));                               // Rv^-1 Dv+^-1 M^-1 (:281)
+    CKI(c.gemm(G, OP_N, c.w.Mp, c.nn, OP_N, c.w.M, c.nn));                                     // G                (:282)
+    return uv_epilogue(c, logdet, sign);                                                       //                  (:285-286)
+}
+
+// inv_invUpV!(G, U, V, ws): exported_functions.jl:324-402
+template <typename T>
+int inv_invUpV_impl(sla_handle_t h, int n, int batch, T* G, const T* UL, const double* Ud, const T* UR,
+                    const T* VL, const double* Vd, const T* VR, double* logdet, T* sign, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.copy(c.w.Mp, UR));                                                                   // :334
+    CKI(c.lu(c.w.Mp, nullptr, 0, 0, nullptr, c.st(3)));                                        // sgn det Ru       (:335)
+    CKI(c.logsum(c.sc(1), Ud, SCALE_MUL_MIN1));                                                // log det Du-      (:343)
+    CKI(c.scale(c.w.Mp, UR, OP_N, Ud, SCALE_MUL_MIN1, nullptr, SCALE_NONE));                   // Du- Ru           (:346-348)
+    CKI(c.copy(c.w.Mpp, VR));                                                                  // :351-352
+    CKI(c.lu(c.w.Mpp, c.w.X, 1, 0, nullptr, c.st(0)));                                         // Rv^-1 -> X       (:353)
+    CKI(c.scale(c.w.X, c.w.X, OP_N, nullptr, SCALE_NONE, Vd, SCALE_DIV_MAX1));                 // Rv^-1 Dv+^-1     (:365)
+    CKI(c.logsum(c.sc(0), Vd, SCALE_MUL_MAX1));                                                // log det Dv+      (:361)
+    CKI(c.gemm(G, OP_N, c.w.Mp, c.nn, OP_N, VL, c.nn, nullptr, 0, Vd, SCALE_MUL_MIN1));        // (Du- Ru Lv) Dv-  (:373-374)
+    CKI(c.gemm(G, OP_C, UL, c.nn, OP_N, c.w.X, c.nn, Ud, SCALE_DIV_MAX1, nullptr, 0, 1));      // += Du+^-1 (Lu^H Rv^-1 Dv+^-1) (:383-387)
+    CKI(c.lu(G, c.w.Mpp, 1, 0, c.sc(2), c.st(2)));                                             // M^-1             (:390-391)
+    CKI(c.gemm(c.w.M, OP_N, c.w.Mpp, c.nn, OP_N, c.w.Mp, c.nn));                               // M^-1 Du- Ru      (:394)
+    CKI(c.gemm(G, OP_N, c.w.X, c.nn, OP_N, c.w.M, c.nn));                                      // G                (:395)
+    CombineArgs<T> a{};
+    a.lterm[0] = c.sc(0); a.lcoef[0] = -1.0;
+    a.lterm[1] = c.sc(2); a.lcoef[1] = 1.0;
+    a.lterm[2] = c.sc(1); a.lcoef[2] = 1.0;   // + log det Du-   (:399)
+    a.nl = 3;
+    a.sterm[0] = c.st(0); a.sterm[1] = c.st(2); a.sterm[2] = c.st(3); a.ns = 3;   // (:398)
+    a.logdet = logdet; a.sign = sign; a.batch = batch;
+    CK(combine_batched<T>(a, c.s));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused chain driver
+// ---------------------------------------------------------------------------------------------
+constexpr size_t BBAR_BUDGET = (size_t)6 << 30;  // bytes for the group-product ping-pong buffers
+
+template <typename T> struct ChainWs {
+    double* ev;
+    T *B0, *B1, *FL, *FR, *FR2, *UL, *UR, *UR2;
+    double *Fd, *Ud2;
+    void* ws;
+    int gc;
+    static int groups_per_chunk(int n, int batch, int ng) {
+        size_t per_group = 2 * (size_t)n * n * batch * sizeof(T);
+        size_t g = BBAR_BUDGET / per_group;
+        if (g < 1) g = 1;
+        return (int)(g > (size_t)ng ? ng : g);
+    }
+    static size_t bytes(int n, int batch, int L, int n_stab) {
+        int ng = L / n_stab;
+        int gc = groups_per_chunk(n, batch, ng);
+        size_t nn = align_up((size_t)n * n * batch * sizeof(T));
+        size_t b = align_up((size_t)batch * L * n * sizeof(double));
+        b += 2 * align_up((size_t)gc * batch * n * n * sizeof(T));
+        b += 6 * nn;
+        b += 2 * align_up((size_t)n * batch * sizeof(double));
+        b += Ws<T>::bytes(n, batch);
+        return b;
+    }
+    ChainWs(void* blob, int n, int batch, int L, int n_stab) {
+        int ng = L / n_stab;
+        gc = groups_per_chunk(n, batch, ng);
+        char* p = static_cast<char*>(blob);
+        size_t nn = align_up((size_t)n * n * batch * sizeof(T));
+        ev = (double*)p; p += align_up((size_t)batch * L * n * sizeof(double));
+        size_t bb = align_up((size_t)gc * batch * n * n * sizeof(T));
+        B0 = (T*)p; p += bb;
+        B1 = (T*)p; p += bb;
+        FL = (T*)p; p += nn; FR = (T*)p; p += nn; FR2 = (T*)p; p += nn;
+        UL = (T*)p; p += nn; UR = (T*)p; p += nn; UR2 = (T*)p; p += nn;
+        Fd = (double*)p; p += align_up((size_t)n * batch * sizeof(double));
+        Ud2 = (double*)p; p += align_up((size_t)n * batch * sizeof(double));
+        ws = p;
+    }
+};
+
+template <typename T>
+int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const T* expK, const signed char* fields,
+                      double lam, int inverse, T* G, double* logdet, T* sign, T* Lout, double* dout, T* Rout,
+                      void* blob, size_t blob_bytes) {
+    if (blob_bytes < ChainWs<T>::bytes(n, batch, L, n_stab)) return -17;
+    ChainWs<T> cw(blob, n, batch, L, n_stab);
+    Ctx<T> c(h, n, batch, cw.ws);
+    const int ng = L / n_stab, gc = cw.gc;
+    const long long nn = c.nn;
+    cudaStream_t s = c.s;
+
+    CK(hs_exp_batched(cw.ev, fields, lam, (long long)batch * L * n, s));
+
+    // two LDR states: F (IpA), or V (first half of the groups) and U (second half) for IpUV
+    T *FL = cw.FL, *FR = cw.FR, *FR2 = cw.FR2;
+    double* Fd = cw.Fd;
+    CKI(set_identity_impl<T>(h, n, batch, FL, Fd, FR));
+    T *UL = cw.UL, *UR = cw.UR, *UR2 = cw.UR2;
+    double* Ud = cw.Ud2;
+    const int half = ng / 2;
+    if (inverse == SLA_INV_IPUV) CKI(set_identity_impl<T>(h, n, batch, UL, Ud, UR));
+
+    for (int g0 = 0; g0 < ng; g0 += gc) {
+        const int gcur = (ng - g0 < gc) ? (ng - g0) : gc;
+        const int bb = batch * gcur;  // group products built in this chunk; index = chain*gcur + gg
+        // X_1 = diag(e_1) expK ; X_i = diag(e_i) (expK X_{i-1})      (test/runtests.jl:93-100)
+        T *cur = cw.B0, *nxt = cw.B1;
+        for (int i = 0; i < n_stab; ++i) {
+            GemmArgs<T> g{};
+            const double* rs0 = cw.ev + ((long long)g0 * n_stab + i) * n;
+            if (i == 0) {
+                // one scale kernel per group of the chunk (row scaling of the shared expK)
+                for (int gg = 0; gg < gcur; ++gg) {
+                    CK(scale_batched<T>(cur + (long long)gg * nn, (long long)gcur * nn, n, expK, 0, n, OP_N,
+                                        rs0 + (long long)gg * n_stab * n, (long long)L * n, SCALE_MUL, nullptr, 0,
+                                        SCALE_NONE, n, batch, s));
+                }
+                continue;
+            }
+            g.A = expK; g.strideA = 0; g.lda = n;
+            g.B = cur; g.strideB = nn; g.ldb = n;
+            g.C = nxt; g.strideC = nn; g.ldc = n;
+            g.M = g.N = g.K = n;
+            g.rs = rs0; g.rs_mode = SCALE_MUL; g.rs_div = gcur; g.stride_rs_hi = (long long)L * n;
+            g.stride_rs = (long long)n_stab * n;
+            g.cs = nullptr; g.cs_mode = SCALE_NONE; g.stride_cs = 0;
+            g.accumulate = 0; g.batch = bb;
+            CK(gemm_batched<T>(OP_N, OP_N, g, s));
+            T* t = cur; cur = nxt; nxt = t;
+        }
+        // stabilised updates  F <- B_bar_g F   (lmul!, overloaded_functions.jl:126-145) with ping-pong R
+        for (int gg = 0; gg < gcur; ++gg) {
+            const int g = g0 + gg;
+            const bool intoU = (inverse == SLA_INV_IPUV) && (g >= half);
+            T*& XL = intoU ? UL : FL;
+            T*& XR = intoU ? UR : FR;
+            T*& XR2 = intoU ? UR2 : FR2;
+            double* Xd = intoU ? Ud : Fd;
+            const T* Bg = cur + (long long)gg * nn;
+            CKI(c.gemm(c.w.M, OP_N, Bg, (long long)gcur * nn, OP_N, XL, nn, nullptr, SCALE_NONE, Xd, SCALE_MUL));
+            CKI(c.ldr(XL, Xd, c.w.Mp, c.w.M, nn));
+            CKI(c.gemm(XR2, OP_N, c.w.Mp, nn, OP_N, XR, nn));
+            T* t = XR; XR = XR2; XR2 = t;
+        }
+    }
+    if (inverse == SLA_INV_IPA) {
+        CKI(inv_IpA_impl<T>(h, n, batch, G, FL, Fd, FR, logdet, sign, cw.ws));
+        if (Lout) CKI(c.copy(Lout, FL));
+        if (dout) CKI(c.copy_d(dout, Fd));
+        if (Rout) CKI(c.copy(Rout, FR));
+        return 0;
+    }
+    return inv_IpUV_impl<T>(h, n, batch, G, UL, Ud, UR, FL, Fd, FR, logdet, sign, cw.ws);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------
+#define CHECK_COMMON(h, dtype, n, batch)                 \
+    do {                                                 \
+        if (!(h)) return -1;                             \
+        if ((dtype) != SLA_F64 && (dtype) != SLA_C64) return -2; \
+        if ((n) <= 0) return -3;                         \
+        if ((batch) < 0) return -4;                      \
+        if ((batch) == 0) return 0;                      \
+    } while (0)
+
+#define DISPATCH(dtype, fn, ...) \
+    ((dtype) == SLA_F64 ? fn<double>(__VA_ARGS__) : fn<cplx>(__VA_ARGS__))
+
+extern "C" {
+
+int sla_version(void) { return 100; }
+
+int sla_create(sla_handle_t* handle, void* stream) {
+    if (!handle) return -1;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    sla_handle_s* h = new (std::nothrow) sla_handle_s;
+    if (!h) return -1;
+    h->stream = static_cast<cudaStream_t>(stream);
+    *handle = h;
+    return 0;
+}
+
+int sla_destroy(sla_handle_t handle) {
+    delete handle;
+    return 0;
+}
+
+int sla_set_stream(sla_handle_t handle, void* stream) {
+    if (!handle) return -1;
+    handle->stream = static_cast<cudaStream_t>(stream);
+    return 0;
+}
+
+size_t sla_workspace_bytes(int dtype, int n, int batch) {
+    if (n <= 0 || batch <= 0) return 0;
+    return dtype == SLA_F64 ? Ws<double>::bytes(n, batch) : Ws<cplx>::bytes(n, batch);
+}
+
+int* sla_workspace_info(void* ws, int dtype, int n, int batch) {
+    if (!ws || n <= 0 || batch <= 0) return nullptr;
+    return dtype == SLA_F64 ? Ws<double>(ws, n, batch).info : Ws<cplx>(ws, n, batch).info;
+}
+
+#define TP(x) static_cast<T*>(x)
+#define CTP(x) static_cast<const T*>(x)
+
+int sla_ldr(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!ws) return -8;
+    if (dtype == SLA_F64) return ldr_impl<double>(h, n, batch, (double*)L, d, (double*)R, ws);
+    return ldr_impl<cplx>(h, n, batch, (cplx*)L, d, (cplx*)R, ws);
+}
+
+int sla_ldr_from(sla_handle_t h, int dtype, int n, int batch, const void* A, long long strideA, void* L, double* d,
+                 void* R, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!A) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10;
+    if (dtype == SLA_F64) return ldr_from_impl<double>(h, n, batch, (const double*)A, strideA, (double*)L, d, (double*)R, ws);
+    return ldr_from_impl<cplx>(h, n, batch, (const cplx*)A, strideA, (cplx*)L, d, (cplx*)R, ws);
+}
+
+int sla_set_identity(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!L) return -5; if (!d) return -6; if (!R) return -7;
+    if (dtype == SLA_F64) return set_identity_impl<double>(h, n, batch, (double*)L, d, (double*)R);
+    return set_identity_impl<cplx>(h, n, batch, (cplx*)L, d, (cplx*)R);
+}
+
+int sla_copy(sla_handle_t h, int dtype, int n, int batch, void* Lo, double* dout, void* Ro, const void* Li,
+             const double* din, const void* Ri) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!Lo) return -5; if (!dout) return -6; if (!Ro) return -7; if (!Li) return -8; if (!din) return -9; if (!Ri) return -10;
+    size_t es = dtype == SLA_F64 ? sizeof(double) : sizeof(cplx);
+    size_t mb = (size_t)n * n * batch * es;
+    CK(cudaMemcpyAsync(Lo, Li, mb, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(dout, din, (size_t)n * batch * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(Ro, Ri, mb, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+int sla_ldr_to_mat(sla_handle_t h, int dtype, int n, int batch, void* A, const void* L, const double* d,
+                   const void* R, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!A) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9;
+    if (dtype == SLA_F64) return ldr_to_mat_impl<double>(h, n, batch, (double*)A, (const double*)L, d, (const double*)R, ws);
+    return ldr_to_mat_impl<cplx>(h, n, batch, (cplx*)A, (const cplx*)L, d, (const cplx*)R, ws);
+}
+
+int sla_adjoint(sla_handle_t h, int dtype, int n, int batch, void* At, const void* L, const double* d, const void* R,
+                void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!At) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9;
+    if (dtype == SLA_F64) return adjoint_impl<double>(h, n, batch, (double*)At, (const double*)L, d, (const double*)R, ws);
+    return adjoint_impl<cplx>(h, n, batch, (cplx*)At, (const cplx*)L, d, (const cplx*)R, ws);
+}
+
+int sla_lmul_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U, long long strideU, void* L,
+                     double* d, void* R, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!U) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10;
+    if (dtype == SLA_F64) return lmul_mat_ldr_impl<double>(h, n, batch, (const double*)U, strideU, (double*)L, d, (double*)R, ws);
+    return lmul_mat_ldr_impl<cplx>(h, n, batch, (const cplx*)U, strideU, (cplx*)L, d, (cplx*)R, ws);
+}
+
+int sla_rmul_ldr_mat(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R, const void* V,
+                     long long strideV, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -10;
+    if (dtype == SLA_F64) return rmul_ldr_mat_impl<double>(h, n, batch, (double*)L, d, (double*)R, (const double*)V, strideV, ws);
+    return rmul_ldr_mat_impl<cplx>(h, n, batch, (cplx*)L, d, (cplx*)R, (const cplx*)V, strideV, ws);
+}
+
+#define UV_NULLCHECK()                                                                           \
+    if (!UL) return -5; if (!Ud) return -6; if (!UR) return -7; if (!VL) return -8; if (!Vd) return -9; \
+    if (!VR) return -10;
+
+int sla_lmul_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, const void* UL, const double* Ud, const void* UR,
+                     void* VL, double* Vd, void* VR, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    UV_NULLCHECK();
+    if (!ws) return -11;
+    if (UL == VL || UR == VR || Ud == Vd) return -8;  // U and V must be distinct (overloaded_functions.jl:179,185)
+    if (dtype == SLA_F64)
+        return lmul_ldr_ldr_impl<double>(h, n, batch, (const double*)UL, Ud, (const double*)UR, (double*)VL, Vd, (double*)VR, ws);
+    return lmul_ldr_ldr_impl<cplx>(h, n, batch, (const cplx*)UL, Ud, (const cplx*)UR, (cplx*)VL, Vd, (cplx*)VR, ws);
+}
+
+int sla_rmul_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, double* Ud, void* UR, const void* VL,
+                     const double* Vd, const void* VR, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    UV_NULLCHECK();
+    if (!ws) return -11;
+    if (UL == VL || UR == VR || Ud == Vd) return -8;
+    if (dtype == SLA_F64)
+        return rmul_ldr_ldr_impl<double>(h, n, batch, (double*)UL, Ud, (double*)UR, (const double*)VL, Vd, (const double*)VR, ws);
+    return rmul_ldr_ldr_impl<cplx>(h, n, batch, (cplx*)UL, Ud, (cplx*)UR, (const cplx*)VL, Vd, (const cplx*)VR, ws);
+}
+
+int sla_lmul_ldr_mat(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
+                     void* V, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -9;
+    if (dtype == SLA_F64) return lmul_ldr_mat_impl<double>(h, n, batch, (const double*)L, d, (const double*)R, (double*)V, ws);
+    return lmul_ldr_mat_impl<cplx>(h, n, batch, (const cplx*)L, d, (const cplx*)R, (cplx*)V, ws);
+}
+
+int sla_rmul_mat_ldr(sla_handle_t h, int dtype, int n, int batch, void* U, const void* L, const double* d,
+                     const void* R, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!U) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9;
+    if (dtype == SLA_F64) return rmul_mat_ldr_impl<double>(h, n, batch, (double*)U, (const double*)L, d, (const double*)R, ws);
+    return rmul_mat_ldr_impl<cplx>(h, n, batch, (cplx*)U, (const cplx*)L, d, (const cplx*)R, ws);
+}
+
+int sla_det_lu(sla_handle_t h, int dtype, int n, int batch, void* A, double* logdet, void* sign, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!A) return -5; if (!ws) return -8;
+    if (dtype == SLA_F64) return det_lu_impl<double>(h, n, batch, (double*)A, logdet, (double*)sign, ws);
+    return det_lu_impl<cplx>(h, n, batch, (cplx*)A, logdet, (cplx*)sign, ws);
+}
+
+int sla_inv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, double* logdet, void* sign, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!A) return -5; if (!ws) return -8;
+    if (dtype == SLA_F64) return inv_lu_impl<double>(h, n, batch, (double*)A, logdet, (double*)sign, ws);
+    return inv_lu_impl<cplx>(h, n, batch, (cplx*)A, logdet, (cplx*)sign, ws);
+}
+
+int sla_logabsdet(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
+                  double* logdet, void* sign, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!ws) return -10;
+    if (dtype == SLA_F64) return logabsdet_impl<double>(h, n, batch, (const double*)L, d, (const double*)R, logdet, (double*)sign, ws);
+    return logabsdet_impl<cplx>(h, n, batch, (const cplx*)L, d, (const cplx*)R, logdet, (cplx*)sign, ws);
+}
+
+int sla_inv_IpA(sla_handle_t h, int dtype, int n, int batch, void* G, const void* L, const double* d, const void* R,
+                double* logdet, void* sign, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!G) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -11;
+    if (dtype == SLA_F64) return inv_IpA_impl<double>(h, n, batch, (double*)G, (const double*)L, d, (const double*)R, logdet, (double*)sign, ws);
+    return inv_IpA_impl<cplx>(h, n, batch, (cplx*)G, (const cplx*)L, d, (const cplx*)R, logdet, (cplx*)sign, ws);
+}
+
+#define DEFINE_UV(name, impl)                                                                                      \
+    int name(sla_handle_t h, int dtype, int n, int batch, void* G, const void* UL, const double* Ud, const void* UR, \
+             const void* VL, const double* Vd, const void* VR, double* logdet, void* sign, void* ws) {             \
+        CHECK_COMMON(h, dtype, n, batch);                                                                          \
+        if (!G) return -5;                                                                                         \
+        if (!UL) return -6; if (!Ud) return -7; if (!UR) return -8; if (!VL) return -9; if (!Vd) return -10;       \
+        if (!VR) return -11; if (!ws) return -14;                                                                  \
+        if (dtype == SLA_F64)                                                                                      \
+            return impl<double>(h, n, batch, (double*)G, (const double*)UL, Ud, (const double*)UR, (const double*)VL, \
+                                Vd, (const double*)VR, logdet, (double*)sign, ws);                                 \
+        return impl<cplx>(h, n, batch, (cplx*)G, (const cplx*)UL, Ud, (const cplx*)UR, (const cplx*)VL, Vd,         \
+                          (const cplx*)VR, logdet, (cplx*)sign, ws);                                               \
+    }
+DEFINE_UV(sla_inv_IpUV, inv_IpUV_impl)
+DEFINE_UV(sla_inv_UpV, inv_UpV_impl)
+DEFINE_UV(sla_inv_invUpV, inv_invUpV_impl)
+
+int sla_gemm(sla_handle_t h, int dtype, int opa, int opb, int m, int n, int k, const void* A, int lda,
+             long long strideA, const void* B, int ldb, long long strideB, void* C, int ldc, long long strideC,
+             int batch, int accumulate) {
+    if (!h) return -1;
+    if (dtype != SLA_F64 && dtype != SLA_C64) return -2;
+    if ((opa != SLA_OP_N && opa != SLA_OP_C)) return -3;
+    if ((opb != SLA_OP_N && opb != SLA_OP_C)) return -4;
+    if (m < 0) return -5; if (n < 0) return -6; if (k < 0) return -7;
+    if (!A) return -8; if (!B) return -11; if (!C) return -14;
+    if (batch < 0) return -17;
+    if (m == 0 || n == 0 || batch == 0) return 0;
+    if (dtype == SLA_F64) {
+        GemmArgs<double> g{};
+        g.A = (const double*)A; g.B = (const double*)B; g.C = (double*)C;
+        g.strideA = strideA; g.strideB = strideB; g.strideC = strideC;
+        g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.M = m; g.N = n; g.K = k;
+        g.accumulate = accumulate; g.batch = batch;
+        CK(gemm_batched<double>(opa, opb, g, h->stream));
+    } else {
+        GemmArgs<cplx> g{};
+        g.A = (const cplx*)A; g.B = (const cplx*)B; g.C = (cplx*)C;
+        g.strideA = strideA; g.strideB = strideB; g.strideC = strideC;
+        g.lda = lda; g.ldb = ldb; g.ldc = ldc; g.M = m; g.N = n; g.K = k;
+        g.accumulate = accumulate; g.batch = batch;
+        CK(gemm_batched<cplx>(opa, opb, g, h->stream));
+    }
+    return 0;
+}
+
+size_t sla_greens_chain_workspace_bytes(int dtype, int n, int batch, int L, int n_stab) {
+    if (n <= 0 || batch <= 0 || L <= 0 || n_stab <= 0 || L % n_stab) return 0;
+    return dtype == SLA_F64 ? ChainWs<double>::bytes(n, batch, L, n_stab) : ChainWs<cplx>::bytes(n, batch, L, n_stab);
+}
+
+int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L, int n_stab, const void* expK,
+                     const signed char* fields, double lam, int inverse, void* G, double* logdet, void* sign,
+                     void* Lout, double* dout, void* Rout, void* ws, size_t ws_bytes) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (L <= 0) return -5;
+    if (n_stab <= 0 || L % n_stab) return -6;
+    if (!expK) return -7; if (!fields) return -8;
+    if (inverse != SLA_INV_IPA && inverse != SLA_INV_IPUV) return -10;
+    if (inverse == SLA_INV_IPUV && (L / n_stab) < 2) return -10;
+    if (!G) return -11; if (!logdet) return -12; if (!sign) return -13; if (!ws) return -17;
+    if (dtype == SLA_F64)
+        return greens_chain_impl<double>(h, n, batch, L, n_stab, (const double*)expK, fields, lam, inverse, (double*)G,
+                                         logdet, (double*)sign, (double*)Lout, dout, (double*)Rout, ws, ws_bytes);
+    return greens_chain_impl<cplx>(h, n, batch, L, n_stab, (const cplx*)expK, fields, lam, inverse, (cplx*)G, logdet,
+                                   (cplx*)sign, (cplx*)Lout, dout, (cplx*)Rout, ws, ws_bytes);
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// Strided-batched column-major GEMM on the FP64 tensor pipe (DMMA.8x8x4) with fused diagonal
+// scaling:   C[b] (+)= rowscale(r[b]) * ( op(A[b]) * op(B[b]) ) * colscale(c[b])
+//
+// This replaces every `mul!(C, A, B)` of the reference (BLAS ?gemm via LinearAlgebra.mul!,
+// e.g. src/overloaded_functions.jl:133,141; src/exported_functions.jl:64,146,158,169,170) together
+// with the `Diagonal` scalings that surround it (overloaded_functions.jl:134-135,
+// exported_functions.jl:41-42,147,155).
+//
+// Design (B200): operands are staged global->shared with cp.async (LDGSTS, .cg so the streams do
+// not pollute L1) through a 3-stage ring; each warp owns a WM x WN register tile built from
+// 8x8 DMMA accumulators.  The MMA is used "transposed" (MMA-M <-> matrix column n, MMA-N <-> matrix
+// row m) so that the two accumulator values a lane owns are adjacent rows of one column of the
+// column-major C and are written with one 16-byte store.  Shared tiles are padded so that the
+// fragment reads (lane t -> [t/4][t%4]) are bank-conflict free for both operand orientations.
+// Complex GEMM runs 4 real DMMAs per tile pair on the interleaved (re,im) data.
+#pragma once
+#include "sla_common.cuh"
+
+namespace sla {
+
+enum Op : int { OP_N = 0, OP_C = 1 };  // OP_C = conjugate transpose (plain transpose for real)
+
+template <typename T> struct GemmArgs {
+    const T* A; const T* B; T* C;
+    long long strideA, strideB, strideC;  // in elements; 0 = operand shared by the whole batch
+    int lda, ldb, ldc;
+    int M, N, K;
+    const double* rs; long long stride_rs; int rs_mode;   // row scaling (length M), may be null
+    int rs_div; long long stride_rs_hi;                    // rs_div>0: rs offset = (b/rs_div)*stride_rs_hi + (b%rs_div)*stride_rs
+    const double* cs; long long stride_cs; int cs_mode;   // column scaling (length N), may be null
+    int accumulate;                                        // C += ... instead of C = ...
+    int batch;
+};
+
+template <typename T> struct TilePad { static constexpr int value = 4; };
+template <> struct TilePad<cplx> { static constexpr int value = 2; };
+
+// One operand tile in shared memory.  IDXC=true : stored [k][idx] (idx contiguous, ld = BIDX+pad)
+//                                     IDXC=false: stored [idx][k] (k contiguous,   ld = BK+pad)
+template <typename T, bool IDXC, int BIDX, int BK> struct OperandTile {
+    static constexpr int PAD = TilePad<T>::value;
+    static constexpr int LD = (IDXC ? BIDX : BK) + PAD;
+    static constexpr int ELEMS = (IDXC ? BK : BIDX) * LD;
+    static constexpr int EPC = 16 / (int)sizeof(T);  // elements per 16-byte chunk
+
+    // global element (idx, k) lives at g[idx*sidx + k*sk] with exactly one of sidx/sk == 1
+    template <int NT>
+    __device__ static __forceinline__ void load(T* s, const T* g, int ld, int idx0, int k0, int idx_max,
+                                                int k_max, bool vec_ok, int tid) {
+        if (IDXC) {
+            constexpr int CPR = BIDX / EPC;  // chunks per k-row
+            constexpr int TOTAL = CPR * BK;
+            for (int c = tid; c < TOTAL; c += NT) {
+                int kk = c / CPR, ii = (c % CPR) * EPC;
+                T* dst = s + kk * LD + ii;
+                int gi = idx0 + ii, gk = k0 + kk;
+                const T* src = g + (long long)gk * ld + gi;
+                int nvalid = (gk < k_max) ? max(0, min(EPC, idx_max - gi)) : 0;
+                copy_chunk(dst, src, nvalid, vec_ok, g);
+            }
+        } else {
+            constexpr int CPR = BK / EPC;  // chunks per idx-row
+            constexpr int TOTAL = CPR * BIDX;
+            for (int c = tid; c < TOTAL; c += NT) {
+                int ii = c / CPR, kk = (c % CPR) * EPC;
+                T* dst = s + ii * LD + kk;
+                int gi = idx0 + ii, gk = k0 + kk;
+                const T* src = g + (long long)gi * ld + gk;
+                int nvalid = (gi < idx_max) ? max(0, min(EPC, k_max - gk)) : 0;
+                copy_chunk(dst, src, nvalid, vec_ok, g);
+            }
+        }
+    }
+    __device__ static __forceinline__ void copy_chunk(T* dst, const T* src, int nvalid, bool vec_ok,
+                                                      const T* safe) {
+        if (vec_ok || EPC == 1) {
+            cp_async16(dst, nvalid > 0 ? (const void*)src : (const void*)safe, nvalid * (int)sizeof(T));
+        } else {  // real data whose rows are only 8-byte aligned (odd ld): two 8-byte copies
+            cp_async8(dst, nvalid > 0 ? (const void*)src : (const void*)safe, nvalid > 0 ? 8 : 0);
+            cp_async8((char*)dst + 8, nvalid > 1 ? (const void*)((const char*)src + 8) : (const void*)safe,
+                      nvalid > 1 ? 8 : 0);
+        }
+    }
+    // fragment element [idx][k]
+    __device__ static __forceinline__ T frag(const T* s, int idx, int k) {
+        return IDXC ? s[k * LD + idx] : s[idx * LD + k];
+    }
+};
+
+// acc(8x8 tile pair) += nfrag (x) mfrag
+__device__ __forceinline__ void mma_tile(double (&acc)[2], double nf, double mf) { dmma884(acc[0], acc[1], nf, mf); }
+__device__ __forceinline__ void mma_tile(cplx (&acc)[2], cplx nf, cplx mf) {
+    dmma884(acc[0].re, acc[1].re, nf.re, mf.re);
+    dmma884(acc[0].re, acc[1].re, -nf.im, mf.im);
+    dmma884(acc[0].im, acc[1].im, nf.re, mf.im);
+    dmma884(acc[0].im, acc[1].im, nf.im, mf.re);
+}
+
+template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(GemmArgs<T> p) {
+    constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
+    constexpr int NT = WARPS_M * WARPS_N * 32;
+    constexpr int MF = WM / 8, NF = WN / 8;
+    // op(A)[m][k]: OP_N -> A(m,k) col-major => m contiguous (IDXC); OP_C -> stored (k,m) => k contiguous
+    using TileA = OperandTile<T, OPA == OP_N, BM, BK>;
+    // op(B)[k][n]: OP_N -> B(k,n) col-major => k contiguous; OP_C -> stored (n,k) => n contiguous (IDXC)
+    using TileB = OperandTile<T, OPB == OP_C, BN, BK>;
+    constexpr int STAGE_ELEMS = TileA::ELEMS + TileB::ELEMS;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+    const int tiles_m = (p.M + BM - 1) / BM;
+    const int tiles = tiles_m * ((p.N + BN - 1) / BN);
+    const int tile = blockIdx.x % tiles;
+    const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+    const int b = blockIdx.x / tiles;
+
+    const T* A = p.A + (long long)b * p.strideA;
+    const T* B = p.B + (long long)b * p.strideB;
+    T* C = p.C + (long long)b * p.strideC;
+    const bool vecA = ((p.lda & 1) == 0) && ((((uintptr_t)A) & 15) == 0);
+    const bool vecB = ((p.ldb & 1) == 0) && ((((uintptr_t)B) & 15) == 0);
+
+    T acc[NF][MF][2];
+#pragma unroll
+    for (int i = 0; i < NF; ++i)
+#pragma unroll
+        for (int j = 0; j < MF; ++j) { acc[i][j][0] = mk<T>(0.0); acc[i][j][1] = mk<T>(0.0); }
+
+    const int KT = (p.K + BK - 1) / BK;
+    auto load_stage = [&](int stage, int kt) {
+        T* sa = smem + stage * STAGE_ELEMS;
+        T* sb = sa + TileA::ELEMS;
+        TileA::template load<NT>(sa, A, p.lda, m0, kt * BK, p.M, p.K, vecA, tid);
+        TileB::template load<NT>(sb, B, p.ldb, n0, kt * BK, p.N, p.K, vecB, tid);
+    };
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < KT) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    const int fi = lane >> 2, fk = lane & 3;
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) load_stage(nk % STAGES, nk);
+            cp_async_commit();
+        }
+        const T* sa = smem + (kt % STAGES) * STAGE_ELEMS;
+        const T* sb = sa + TileA::ELEMS;
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            T nf[NF], mf[MF];
+#pragma unroll
+            for (int i = 0; i < NF; ++i) {
+                T v = TileB::frag(sb, wn * WN + i * 8 + fi, kk + fk);
+                nf[i] = (OPB == OP_C) ? conj_(v) : v;
+            }
+#pragma unroll
+            for (int j = 0; j < MF; ++j) {
+                T v = TileA::frag(sa, wm * WM + j * 8 + fi, kk + fk);
+                mf[j] = (OPA == OP_C) ? conj_(v) : v;
+            }
+#pragma unroll
+            for (int i = 0; i < NF; ++i)
+#pragma unroll
+                for (int j = 0; j < MF; ++j) mma_tile(acc[i][j], nf[i], mf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: lane owns C[m, m+1][n] with m = m0 + wm*WM + j*8 + 2*(lane&3), n = n0 + wn*WN + i*8 + lane/4
+    const double* rs = nullptr;
+    if (p.rs) rs = (p.rs_div > 0) ? p.rs + (long long)(b / p.rs_div) * p.stride_rs_hi + (long long)(b % p.rs_div) * p.stride_rs
+                                  : p.rs + (long long)b * p.stride_rs;
+    const double* cs = p.cs ? p.cs + (long long)b * p.stride_cs : nullptr;
+    const bool vecC = ((p.ldc & 1) == 0 || sizeof(T) == 16) && ((((uintptr_t)C) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+        const int n = n0 + wn * WN + i * 8 + fi;
+        if (n >= p.N) continue;
+        const double csv = cs ? cs[n] : 1.0;
+#pragma unroll
+        for (int j = 0; j < MF; ++j) {
+            const int m = m0 + wm * WM + j * 8 + 2 * fk;
+            if (m >= p.M) continue;
+            T* dst = C + (long long)n * p.ldc + m;
+            T v0 = acc[i][j][0], v1 = acc[i][j][1];
+            const bool has1 = (m + 1 < p.M);
+            if (rs) {
+                v0 = apply_scale(v0, rs[m], p.rs_mode);
+                if (has1) v1 = apply_scale(v1, rs[m + 1], p.rs_mode);
+            }
+            if (cs) {
+                v0 = apply_scale(v0, csv, p.cs_mode);
+                v1 = apply_scale(v1, csv, p.cs_mode);
+            }
+            bool done = false;
+            if constexpr (sizeof(T) == 8) {
+                if (vecC && has1) {
+                    double2* d2 = reinterpret_cast<double2*>(dst);
+                    if (p.accumulate) {
+                        double2 o = *d2;
+                        v0 = v0 + o.x;
+                        v1 = v1 + o.y;
+                    }
+                    *d2 = make_double2(v0, v1);
+                    done = true;
+                }
+            }
+            if (!done) {
+                if (p.accumulate) {
+                    v0 = v0 + dst[0];
+                    if (has1) v1 = v1 + dst[1];
+                }
+                dst[0] = v0;
+                if (has1) dst[1] = v1;
+            }
+        }
+    }
+}
+
+template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES>
+static cudaError_t launch_gemm_cfg(const GemmArgs<T>& p, cudaStream_t stream) {
+    using TileA = OperandTile<T, OPA == OP_N, BM, BK>;
+    using TileB = OperandTile<T, OPB == OP_C, BN, BK>;
+    constexpr int SMEM = STAGES * (TileA::ELEMS + TileB::ELEMS) * (int)sizeof(T);
+    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    auto kern = gemm_kernel<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+    if (tiles <= 0 || p.batch <= 0) return cudaSuccess;
+    kern<<<(unsigned)((long long)tiles * p.batch), NT, SMEM, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace sla

@@ -1,0 +1,58 @@
+// Internal (C++) interface between the kernel translation units and the C-ABI layer.
+#pragma once
+#include "sla_gemm.cuh"
+
+namespace sla {
+
+template <typename T> cudaError_t gemm_batched(int opa, int opb, const GemmArgs<T>& p, cudaStream_t s);
+
+// ---- LDR factorisation (sla_ldr.cu) -------------------------------------------------------
+template <typename T> struct LdrArgs {
+    T* L; long long strideL; int ldl;        // in: matrix to factor, out: Q (unitary)
+    const T* Ain; long long strideAin; int ldain;  // optional separate input (copied into L while the norms are read)
+    double* d; long long stride_d;           // out: |diag R'|
+    T* R; long long strideR; int ldr;        // out: D^-1 R' P^T
+    T* Twork; long long strideT;             // scratch: ldr_twork_elems(n) elements per matrix
+    long long* jpvt_out;                     // optional: 1-based pivots (n per matrix), may be null
+    int n; int batch;
+};
+template <typename T> cudaError_t ldr_batched(const LdrArgs<T>& p, cudaStream_t s);
+template <typename T> size_t ldr_twork_elems(int n);
+
+// ---- LU / inverse with log|det| and sign (sla_lu.cu) ----------------------------------------
+template <typename T> struct LuArgs {
+    T* A; long long strideA; int lda;        // in: matrix; out: LU factors (invert=0) or A^-1 (invert=1, copy_back=1)
+    T* X; long long strideX; int ldx;        // invert=1: receives A^-1 (scratch n*n per matrix)
+    double* logdet; T* sign;                 // per matrix; det A (invert=0) or det A^-1 (invert=1); may be null
+    long long* ipiv_out;                     // optional 1-based pivots
+    int* info;                               // optional per-matrix: 0 ok, k>0 = U(k,k) exactly zero
+    int invert, copy_back;
+    int n; int batch;
+};
+template <typename T> cudaError_t lu_batched(const LuArgs<T>& p, cudaStream_t s);
+
+// ---- element-wise / small kernels (sla_ops.cu) ---------------------------------------------
+// dst = rowscale(rs) * op(src) * colscale(cs); src may be shared (stride 0); op in {OP_N, OP_C}
+template <typename T>
+cudaError_t scale_batched(T* dst, long long sdst, int lddst, const T* src, long long ssrc, int ldsrc, int op,
+                          const double* rs, long long srs, int rs_mode, const double* cs, long long scs,
+                          int cs_mode, int n, int batch, cudaStream_t s);
+template <typename T>
+cudaError_t set_identity_batched(T* A, long long sA, int lda, int n, int batch, cudaStream_t s);
+cudaError_t fill_batched(double* d, double value, long long count, cudaStream_t s);
+// M = L*diag(min(d,1)) + Rinv*diag(1/max(d,1));  Rinv <- Rinv*diag(1/max(d,1))   (exported_functions.jl:37-57)
+template <typename T>
+cudaError_t ipa_combine_batched(T* M, T* Rinv, const T* L, const double* d, int n, int batch, cudaStream_t s);
+// out[b] = sum_i log(f(d[b,i])),  f by ScaleMode (NONE: d, MUL_MAX1: max(d,1), MUL_MIN1: min(d,1))
+cudaError_t logsum_batched(double* out, const double* d, long long sd, int mode, int n, int batch, cudaStream_t s);
+// logdet[b] = sum_k coef[k]*terms[k][b];  sign[b] = prod_k (conj_k ? conj : id)(signs[k][b])
+template <typename T> struct CombineArgs {
+    const double* lterm[4]; double lcoef[4]; int nl;
+    const T* sterm[4]; int sconj[4]; int ns;
+    double* logdet; T* sign; int batch;
+};
+template <typename T> cudaError_t combine_batched(const CombineArgs<T>& a, cudaStream_t s);
+// ev[c,l,i] = exp(lam * s[c,l,i])
+cudaError_t hs_exp_batched(double* ev, const signed char* fields, double lam, long long count, cudaStream_t s);
+
+}  // namespace sla

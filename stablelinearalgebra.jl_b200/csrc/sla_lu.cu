@@ -1,0 +1,308 @@
+// Batched partial-pivot LU with fused log|det| / sign, and the LU-based inverse.
+//
+// Replaces det_lu! (src/lu.jl:123-140: getrf! + diagonal/pivot scan) and inv_lu! (src/lu.jl:149-158:
+// det_lu! + getri!) -- LAPACK ?getrf / ?getri behind src/lu.jl:63-93 -- with one kernel launch per
+// batch: one CTA owns one matrix.  Right-looking blocked LU: the NB-column panel is factorised in
+// shared memory (pivot search = block-wide argmax with "first maximal index" tie-break like i?amax),
+// the panel's row interchanges are applied to the rest of the matrix as one gathered permutation,
+// U12 comes from a register-resident forward substitution and the rank-NB trailing update runs on
+// DMMA from the shared panels.  The inverse is formed as X = U^-1 (L^-1 P) by two blocked triangular
+// sweeps built from the same pieces (mathematically the same inverse ?getri returns).
+#include "sla_cta.cuh"
+#include "sla_kernels.h"
+
+namespace sla {
+
+namespace {
+
+constexpr int LU_NB = 32;
+
+template <typename T> __host__ __device__ inline size_t lu_smem_bytes(int n, int NB) {
+    size_t ld = panel_ld<T>(n);
+    size_t b = 2 * NB * ld * sizeof(T);       // Ps, Us
+    b += 32 * sizeof(double) + 32 * sizeof(T);  // redv, redt
+    b += (size_t)n * sizeof(int) * 2;         // ipiv, rowpos
+    b += (4 * NB + 64) * sizeof(int);         // touched rows, sources, redi, misc
+    return b + 64;
+}
+
+template <typename T, int NB>
+__device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int ld, int* ipiv, int* rowpos,
+                          int* tl, int* tsrc, double* redv, int* redi, int* misc, int* info_out) {
+    const int tid = threadIdx.x;
+    for (int r = tid; r < n; r += CTA_THREADS) rowpos[r] = -1;
+    for (int p0 = 0; p0 < n; p0 += NB) {
+        const int jb = min(NB, n - p0), kend = p0 + jb;
+        // ---- load panel rows [p0, n)
+        for (int i = 0; i < NB; ++i) {
+            for (int r = tid; r < n; r += CTA_THREADS)
+                Ps[(size_t)i * ld + r] = (i < jb && r >= p0) ? A[(long long)(p0 + i) * lda + r] : mk<T>(0.0);
+        }
+        __syncthreads();
+        // ---- unblocked LU of the panel in shared memory
+        for (int j = 0; j < jb; ++j) {
+            const int k = p0 + j;
+            T* colj = Ps + (size_t)j * ld;
+            double bv = -1.0; int bi = 0x7fffffff;
+            for (int r = k + tid; r < n; r += CTA_THREADS) {
+                double v = abs1_(colj[r]);
+                if (v > bv) { bv = v; bi = r; }
+            }
+            int piv = block_argmax(bv, bi, redv, redi);
+            if (piv >= n) piv = k;  // NaN guard
+            if (tid < jb && piv != k) {
+                T* ci = Ps + (size_t)tid * ld;
+                T t = ci[k]; ci[k] = ci[piv]; ci[piv] = t;
+            }
+            if (tid == 0) ipiv[k] = piv;
+            __syncthreads();
+            const T pv = colj[k];
+            if (is_zero(pv)) {
+                if (tid == 0 && info_out && *info_out == 0) *info_out = k + 1;
+            } else {
+                for (int r = k + 1 + tid; r < n; r += CTA_THREADS) {
+                    T l = colj[r] / pv;
+                    colj[r] = l;
+                    for (int i = j + 1; i < jb; ++i) fms(Ps[(size_t)i * ld + r], l, Ps[(size_t)i * ld + k]);
+                }
+            }
+            __syncthreads();
+        }
+        // ---- panel back to global
+        for (int i = 0; i < jb; ++i)
+            for (int r = p0 + tid; r < n; r += CTA_THREADS) A[(long long)(p0 + i) * lda + r] = Ps[(size_t)i * ld + r];
+        // ---- net row permutation of this panel (thread 0 simulates the jb interchanges)
+        if (tid == 0) {
+            int nt = jb;
+            for (int q = 0; q < jb; ++q) { tl[q] = p0 + q; tsrc[q] = p0 + q; rowpos[p0 + q] = q; }
+            for (int j = 0; j < jb; ++j) {
+                int pj = ipiv[p0 + j];
+                if (pj == p0 + j) continue;
+                int pos = rowpos[pj];
+                if (pos < 0) { pos = nt++; tl[pos] = pj; tsrc[pos] = pj; rowpos[pj] = pos; }
+                int t = tsrc[j]; tsrc[j] = tsrc[pos]; tsrc[pos] = t;
+            }
+            for (int q = 0; q < nt; ++q) rowpos[tl[q]] = -1;
+            misc[0] = nt;
+        }
+        __syncthreads();
+        {
+            const int nt = misc[0];
+            const int ncols_out = n - jb;             // columns outside the panel: [0,p0) U [kend,n)
+            const int ch = (NB * ld) / (2 * NB);      // columns per chunk staged through Us ([q][cl], q < 2*NB)
+            for (int cb = 0; cb < ncols_out; cb += ch) {
+                const int cn = min(ch, ncols_out - cb);
+                for (int e = tid; e < cn * nt; e += CTA_THREADS) {
+                    int q = e / cn, cl = e % cn;
+                    int c = cb + cl; c = (c < p0) ? c : c + jb;
+                    Us[(size_t)q * ch + cl] = A[(long long)c * lda + tsrc[q]];
+                }
+                __syncthreads();
+                for (int e = tid; e < cn * nt; e += CTA_THREADS) {
+                    int q = e / cn, cl = e % cn;
+                    if (tsrc[q] == tl[q]) continue;
+                    int c = cb + cl; c = (c < p0) ? c : c + jb;
+                    A[(long long)c * lda + tl[q]] = Us[(size_t)q * ch + cl];
+                }
+                __syncthreads();
+            }
+        }
+        if (kend < n) {
+            // ---- U12 = L11^-1 A12  (thread per column, registers)
+            for (int c = kend + tid; c < n; c += CTA_THREADS) {
+                T a[NB];
+                T* col = A + (long long)c * lda + p0;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) a[i] = (i < jb) ? col[i] : mk<T>(0.0);
+#pragma unroll
+                for (int i = 1; i < NB; ++i) {
+                    if (i < jb) {
+#pragma unroll
+                        for (int q = 0; q < i; ++q) fms(a[i], Ps[(size_t)q * ld + p0 + i], a[q]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    if (i < jb) col[i] = a[i];
+                    Us[(size_t)i * ld + c] = a[i];
+                }
+            }
+            __syncthreads();
+            cta_rank_update<T, false>(A, lda, kend, n, kend, n, Ps, Us, ld, jb, n - 1);
+            __syncthreads();
+        }
+    }
+}
+
+// logdet = sum log|u_ii|, sgn = prod sign(u_ii) * (-1)^{#interchanges}   (src/lu.jl:128-139)
+template <typename T>
+__device__ void lu_logdet(const T* __restrict__ A, int lda, int n, const int* ipiv, double* redv, T* redt,
+                          double& logdet, T& sgn) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double ld_acc = 0.0;
+    T sg = mk<T>(1.0);
+    for (int i = tid; i < n; i += CTA_THREADS) {
+        T u = A[(long long)i * lda + i];
+        ld_acc += log(abs_(u));
+        sg = sg * sign_(u);
+        if (ipiv[i] != i) sg = -sg;
+    }
+    ld_acc = warp_sum(ld_acc);
+    for (int o = 16; o > 0; o >>= 1) {
+        T other;
+        if constexpr (sizeof(T) == 8) other = __shfl_xor_sync(0xffffffffu, sg, o);
+        else { other.re = __shfl_xor_sync(0xffffffffu, sg.re, o); other.im = __shfl_xor_sync(0xffffffffu, sg.im, o); }
+        sg = sg * other;
+    }
+    if (lane == 0) { redv[warp] = ld_acc; redt[warp] = sg; }
+    __syncthreads();
+    logdet = 0.0;
+    sgn = mk<T>(1.0);
+    for (int w = 0; w < CTA_WARPS; ++w) { logdet += redv[w]; sgn = sgn * redt[w]; }
+    __syncthreads();
+}
+
+template <typename T, int NB>
+__device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restrict__ X, int ldx, T* Ps, T* Us,
+                           int ld, const int* ipiv, int* rowpos) {
+    const int tid = threadIdx.x;
+    // X = P (row-permuted identity): row r of P*I is e_{src(r)}
+    for (int r = tid; r < n; r += CTA_THREADS) rowpos[r] = r;
+    __syncthreads();
+    if (tid == 0)
+        for (int k = 0; k < n; ++k) {
+            int pk = ipiv[k];
+            if (pk != k) { int t = rowpos[k]; rowpos[k] = rowpos[pk]; rowpos[pk] = t; }
+        }
+    __syncthreads();
+    for (int c = tid >> 5; c < n; c += CTA_WARPS)
+        for (int r = (tid & 31); r < n; r += 32) X[(long long)c * ldx + r] = mk<T>(rowpos[r] == c ? 1.0 : 0.0);
+    __syncthreads();
+    // ---- forward sweep: Y = L^-1 P
+    for (int p0 = 0; p0 < n; p0 += NB) {
+        const int jb = min(NB, n - p0), kend = p0 + jb;
+        for (int i = 0; i < NB; ++i)
+            for (int r = tid; r < n; r += CTA_THREADS)
+                Ps[(size_t)i * ld + r] = (i < jb && r > p0 + i) ? A[(long long)(p0 + i) * lda + r] : mk<T>(0.0);
+        __syncthreads();
+        for (int c = tid; c < n; c += CTA_THREADS) {
+            T a[NB];
+            T* col = X + (long long)c * ldx + p0;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) a[i] = (i < jb) ? col[i] : mk<T>(0.0);
+#pragma unroll
+            for (int i = 1; i < NB; ++i) {
+                if (i < jb) {
+#pragma unroll
+                    for (int q = 0; q < i; ++q) fms(a[i], Ps[(size_t)q * ld + p0 + i], a[q]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                if (i < jb) col[i] = a[i];
+                Us[(size_t)i * ld + c] = a[i];
+            }
+        }
+        __syncthreads();
+        cta_rank_update<T, false>(X, ldx, kend, n, 0, n, Ps, Us, ld, jb, n - 1);
+        __syncthreads();
+    }
+    // ---- backward sweep: X = U^-1 Y
+    const int npan = (n + NB - 1) / NB;
+    for (int pi = npan - 1; pi >= 0; --pi) {
+        const int p0 = pi * NB, jb = min(NB, n - p0);
+        for (int i = 0; i < NB; ++i)
+            for (int r = tid; r < n; r += CTA_THREADS)
+                Ps[(size_t)i * ld + r] = (i < jb && r <= p0 + i) ? A[(long long)(p0 + i) * lda + r] : mk<T>(0.0);
+        __syncthreads();
+        for (int c = tid; c < n; c += CTA_THREADS) {
+            T a[NB];
+            T* col = X + (long long)c * ldx + p0;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) a[i] = (i < jb) ? col[i] : mk<T>(0.0);
+#pragma unroll
+            for (int i = NB - 1; i >= 0; --i) {
+                if (i < jb) {
+#pragma unroll
+                    for (int q = i + 1; q < NB; ++q)
+                        if (q < jb) fms(a[i], Ps[(size_t)q * ld + p0 + i], a[q]);
+                    a[i] = a[i] / Ps[(size_t)i * ld + p0 + i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                if (i < jb) col[i] = a[i];
+                Us[(size_t)i * ld + c] = a[i];
+            }
+        }
+        __syncthreads();
+        cta_rank_update<T, false>(X, ldx, 0, p0, 0, n, Ps, Us, ld, jb, n - 1);
+        __syncthreads();
+    }
+}
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(CTA_THREADS, 1) lu_kernel(LuArgs<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, b = blockIdx.x, tid = threadIdx.x;
+    const int ld = panel_ld<T>(n);
+    T* Ps = reinterpret_cast<T*>(smem_raw);
+    T* Us = Ps + (size_t)NB * ld;
+    T* redt = Us + (size_t)NB * ld;
+    double* redv = reinterpret_cast<double*>(redt + 32);
+    int* ipiv = reinterpret_cast<int*>(redv + 32);
+    int* rowpos = ipiv + n;
+    int* tl = rowpos + n;
+    int* tsrc = tl + 2 * NB;
+    int* redi = tsrc + 2 * NB;
+    int* misc = redi + 32;
+
+    T* A = p.A + (long long)b * p.strideA;
+    int* info = p.info ? p.info + b : nullptr;
+    if (info && tid == 0) *info = 0;
+    __syncthreads();
+    lu_factor<T, NB>(A, p.lda, n, Ps, Us, ld, ipiv, rowpos, tl, tsrc, redv, redi, misc, info);
+    double logdet; T sgn;
+    lu_logdet<T>(A, p.lda, n, ipiv, redv, redt, logdet, sgn);
+    if (p.ipiv_out)
+        for (int i = tid; i < n; i += CTA_THREADS) p.ipiv_out[(long long)b * n + i] = ipiv[i] + 1;
+    if (p.invert) {
+        T* X = p.X + (long long)b * p.strideX;
+        lu_inverse<T, NB>(A, p.lda, n, X, p.ldx, Ps, Us, ld, ipiv, rowpos);
+        if (p.copy_back) {
+            for (int c = tid >> 5; c < n; c += CTA_WARPS)
+                for (int r = (tid & 31); r < n; r += 32) A[(long long)c * p.lda + r] = X[(long long)c * p.ldx + r];
+        }
+        logdet = -logdet;      // src/lu.jl:157
+        sgn = conj_(sgn);
+    }
+    if (tid == 0) {
+        if (p.logdet) p.logdet[b] = logdet;
+        if (p.sign) p.sign[b] = sgn;
+    }
+}
+
+}  // namespace
+
+template <typename T> cudaError_t lu_batched(const LuArgs<T>& p, cudaStream_t stream) {
+    if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
+    int nb = (sizeof(T) == 8) ? LU_NB : LU_NB / 2;  // register-resident substitution columns: a[NB]
+    const size_t limit = 227 * 1024;
+    while (nb >= 8 && lu_smem_bytes<T>(p.n, nb) > limit) nb >>= 1;
+    if (nb < 8) return cudaErrorInvalidValue;
+    size_t smem = lu_smem_bytes<T>(p.n, nb);
+    auto launch = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<p.batch, CTA_THREADS, smem, stream>>>(p);
+        return cudaGetLastError();
+    };
+    if (nb == 32) return launch(lu_kernel<T, 32>);
+    if (nb == 16) return launch(lu_kernel<T, 16>);
+    return launch(lu_kernel<T, 8>);
+}
+
+template cudaError_t lu_batched<double>(const LuArgs<double>&, cudaStream_t);
+template cudaError_t lu_batched<cplx>(const LuArgs<cplx>&, cudaStream_t);
+
+}  // namespace sla
