@@ -49,6 +49,8 @@ extern "C" {
 typedef struct sla_handle_s* sla_handle_t;
 
 SLA_API int sla_version(void);
+/* kernels launched by this library in this process so far (diagnostics; bench.py reports the per-step delta) */
+SLA_API unsigned long long sla_launch_count(void);
 /* stream: a cudaStream_t (0 = legacy default stream). */
 SLA_API int sla_create(sla_handle_t* handle, void* stream);
 SLA_API int sla_destroy(sla_handle_t handle);

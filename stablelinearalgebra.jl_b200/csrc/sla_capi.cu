@@ -501,6 +501,8 @@ extern "C" {
 
 int sla_version(void) { return 100; }
 
+unsigned long long sla_launch_count(void) { return g_launch_count; }
+
 int sla_create(sla_handle_t* handle, void* stream) {
     if (!handle) return -1;
     int dev = 0;

@@ -18,6 +18,9 @@
 
 namespace sla {
 
+// number of kernels this library has launched in this process (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+
 enum Op : int { OP_N = 0, OP_C = 1 };  // OP_C = conjugate transpose (plain transpose for real)
 
 template <typename T> struct GemmArgs {
@@ -243,6 +246,7 @@ static cudaError_t launch_gemm_cfg(const GemmArgs<T>& p, cudaStream_t stream) {
     int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     if (tiles <= 0 || p.batch <= 0) return cudaSuccess;
     kern<<<(unsigned)((long long)tiles * p.batch), NT, SMEM, stream>>>(p);
+    ++g_launch_count;
     return cudaGetLastError();
 }
 

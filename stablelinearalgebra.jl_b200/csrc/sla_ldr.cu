@@ -429,6 +429,7 @@ template <typename T, int NB> static cudaError_t launch_ldr_nb(const LdrArgs<T>&
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<p.batch, CTA_THREADS, smem, stream>>>(p);
+    ++g_launch_count;
     return cudaGetLastError();
 }
 

@@ -295,6 +295,7 @@ template <typename T> cudaError_t lu_batched(const LuArgs<T>& p, cudaStream_t st
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         kern<<<p.batch, CTA_THREADS, smem, stream>>>(p);
+        ++g_launch_count;
         return cudaGetLastError();
     };
     if (nb == 32) return launch(lu_kernel<T, 32>);

@@ -5,6 +5,8 @@
 
 namespace sla {
 
+unsigned long long g_launch_count = 0;
+
 namespace {
 
 template <typename T>
@@ -138,6 +140,7 @@ cudaError_t scale_batched(T* dst, long long sdst, int lddst, const T* src, long 
         scale_kernel<T><<<grid, 256, 0, s>>>(dst + (long long)b0 * sdst, sdst, lddst, src + (long long)b0 * ssrc, ssrc,
                                               ldsrc, op, rs ? rs + (long long)b0 * srs : nullptr, srs, rs_mode,
                                               cs ? cs + (long long)b0 * scs : nullptr, scs, cs_mode, n);
+        ++g_launch_count;
     }
     return cudaGetLastError();
 }
@@ -148,6 +151,7 @@ cudaError_t set_identity_batched(T* A, long long sA, int lda, int n, int batch, 
     for (int b0 = 0; b0 < batch; b0 += 65535) {
         int nb = min(65535, batch - b0);
         identity_kernel<T><<<grid_rows_cols(n, nb, 256), 256, 0, s>>>(A + (long long)b0 * sA, sA, lda, n);
+        ++g_launch_count;
     }
     return cudaGetLastError();
 }
@@ -155,6 +159,7 @@ cudaError_t set_identity_batched(T* A, long long sA, int lda, int n, int batch, 
 cudaError_t fill_batched(double* d, double value, long long count, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
     fill_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(d, value, count);
+    ++g_launch_count;
     return cudaGetLastError();
 }
 
@@ -166,6 +171,7 @@ cudaError_t ipa_combine_batched(T* M, T* Rinv, const T* L, const double* d, int 
         long long off = (long long)b0 * n * n;
         ipa_combine_kernel<T><<<grid_rows_cols(n, nb, 256), 256, 0, s>>>(M + off, Rinv + off, L + off,
                                                                           d + (long long)b0 * n, n);
+        ++g_launch_count;
     }
     return cudaGetLastError();
 }
@@ -173,18 +179,21 @@ cudaError_t ipa_combine_batched(T* M, T* Rinv, const T* L, const double* d, int 
 cudaError_t logsum_batched(double* out, const double* d, long long sd, int mode, int n, int batch, cudaStream_t s) {
     if (batch <= 0) return cudaSuccess;
     logsum_kernel<<<batch, 256, 0, s>>>(out, d, sd, mode, n);
+    ++g_launch_count;
     return cudaGetLastError();
 }
 
 template <typename T> cudaError_t combine_batched(const CombineArgs<T>& a, cudaStream_t s) {
     if (a.batch <= 0) return cudaSuccess;
     combine_kernel<T><<<(a.batch + 127) / 128, 128, 0, s>>>(a);
+    ++g_launch_count;
     return cudaGetLastError();
 }
 
 cudaError_t hs_exp_batched(double* ev, const signed char* fields, double lam, long long count, cudaStream_t s) {
     if (count <= 0) return cudaSuccess;
     hs_exp_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(ev, fields, exp(lam), exp(-lam), count);
+    ++g_launch_count;
     return cudaGetLastError();
 }
 
