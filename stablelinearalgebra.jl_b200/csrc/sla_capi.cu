@@ -3,6 +3,7 @@
 // element-wise helpers) into the reference's operations.  Every composition cites the reference lines
 // it reproduces; scratch use follows the reference's M / M' / M'' roles where that matters for the
 // documented aliasing rules.
+#include <cstdlib>
 #include <new>
 
 #include "../../include/sla_b200.h"
@@ -105,7 +106,10 @@ template <typename T> struct Ctx {
         a.Twork = w.Tw; a.strideT = (long long)w.tw_elems;
         a.jpvt_out = nullptr;
         a.n = n; a.batch = batch;
-        CK(ldr_batched<T>(a, s));
+        // on-chip cluster kernel when the matrix fits the shared memory of <= 8 CTAs, else the L2-streaming one
+        static const bool force_v1 = getenv("SLA_LDR_STREAMING") != nullptr;
+        if (!force_v1 && ldr_cluster_size<T>(n) > 0) CK(ldr_cluster_batched<T>(a, s));
+        else CK(ldr_batched<T>(a, s));
         return 0;
     }
     // LU of A (destroyed).  invert: A^-1 -> X (and back into A if copy_back)

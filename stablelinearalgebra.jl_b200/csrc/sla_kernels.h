@@ -18,6 +18,9 @@ template <typename T> struct LdrArgs {
 };
 template <typename T> cudaError_t ldr_batched(const LdrArgs<T>& p, cudaStream_t s);
 template <typename T> size_t ldr_twork_elems(int n);
+// on-chip (thread-block cluster + DSMEM) version, sla_ldr_cluster.cu; cluster size 0 = matrix too large
+template <typename T> cudaError_t ldr_cluster_batched(const LdrArgs<T>& p, cudaStream_t s);
+template <typename T> int ldr_cluster_size(int n);
 
 // ---- LU / inverse with log|det| and sign (sla_lu.cu) ----------------------------------------
 template <typename T> struct LuArgs {

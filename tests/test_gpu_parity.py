@@ -420,3 +420,18 @@ def test_full_size_properties_C2(S):
     assert torch.equal(G2, G) and torch.equal(ld2, logdet) and torch.equal(sg2, sign)
     # (4) eigenvalues of G lie in [0,1] up to noise for this (sign-problem-free at half filling) model
     assert np.isfinite(Gh).all()
+
+
+def test_streaming_ldr_kernel_subprocess():
+    """The L2-streaming LDR kernel (used when a matrix does not fit a cluster's shared memory, e.g.
+    N=1024) is forced through SLA_LDR_STREAMING=1 in a child process and must pass the same checks."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("SLA_LDR_STREAMING"):
+        pytest.skip("already in the child")
+    env = dict(os.environ, SLA_LDR_STREAMING="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
+                        "ldr_random or ldr_graded or ldr_identity or chain_C1 or ref_lmul_matrix or small_complex"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
