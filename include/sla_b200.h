@@ -51,6 +51,9 @@ typedef struct sla_handle_s* sla_handle_t;
 SLA_API int sla_version(void);
 /* kernels launched by this library in this process so far (diagnostics; bench.py reports the per-step delta) */
 SLA_API unsigned long long sla_launch_count(void);
+/* diagnostics: device buffer of 128 int64 that the cluster LDR kernel fills with per-phase cycle counters
+ * of cluster 0 (NULL switches it off, the default) */
+SLA_API void sla_debug_set_ldr_prof(void* dev_buffer_128_int64);
 /* stream: a cudaStream_t (0 = legacy default stream). */
 SLA_API int sla_create(sla_handle_t* handle, void* stream);
 SLA_API int sla_destroy(sla_handle_t handle);

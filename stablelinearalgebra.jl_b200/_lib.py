@@ -21,6 +21,7 @@ _common = [_vp, _i, _i, _i]  # handle, dtype, n, batch
 SIGNATURES = {
     "sla_version": (_i, []),
     "sla_launch_count": (C.c_ulonglong, []),
+    "sla_debug_set_ldr_prof": (None, [_vp]),
     "sla_create": (_i, [C.POINTER(_vp), _vp]),
     "sla_destroy": (_i, [_vp]),
     "sla_set_stream": (_i, [_vp, _vp]),

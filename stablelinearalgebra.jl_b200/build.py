@@ -34,12 +34,13 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
+    extra = os.environ.get("SLA_NVCC_EXTRA", "").split()   # e.g. -DSLA_LDR_PROFILE for profiles/ldr_phase_cycles.py
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         srcp = os.path.join(CSRC, src)
         if force or _stale(obj, [srcp] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", srcp, "-o", obj]
+            cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", srcp, "-o", obj]
             if verbose:
                 print(" ".join(cmd), file=sys.stderr)
             r = subprocess.run(cmd, capture_output=True, text=True)

@@ -11,6 +11,8 @@
 
 using namespace sla;
 
+static long long* g_ldr_prof = nullptr;   // diagnostics only (sla_debug_set_ldr_prof)
+
 struct sla_handle_s {
     cudaStream_t stream;
 };
@@ -105,6 +107,7 @@ template <typename T> struct Ctx {
         a.R = Rout; a.strideR = nn; a.ldr = n;
         a.Twork = w.Tw; a.strideT = (long long)w.tw_elems;
         a.jpvt_out = nullptr;
+        a.prof = g_ldr_prof;
         a.n = n; a.batch = batch;
         // on-chip cluster kernel when the matrix fits the shared memory of <= 8 CTAs, else the L2-streaming one
         static const bool force_v1 = getenv("SLA_LDR_STREAMING") != nullptr;
@@ -506,6 +509,8 @@ extern "C" {
 int sla_version(void) { return 100; }
 
 unsigned long long sla_launch_count(void) { return g_launch_count; }
+
+void sla_debug_set_ldr_prof(void* dev_buffer_128_int64) { g_ldr_prof = static_cast<long long*>(dev_buffer_128_int64); }
 
 int sla_create(sla_handle_t* handle, void* stream) {
     if (!handle) return -1;

@@ -14,6 +14,7 @@ template <typename T> struct LdrArgs {
     T* R; long long strideR; int ldr;        // out: D^-1 R' P^T
     T* Twork; long long strideT;             // scratch: ldr_twork_elems(n) elements per matrix
     long long* jpvt_out;                     // optional: 1-based pivots (n per matrix), may be null
+    long long* prof;                         // optional (diagnostics): per-phase cycle counters of cluster 0, may be null
     int n; int batch;
 };
 template <typename T> cudaError_t ldr_batched(const LdrArgs<T>& p, cudaStream_t s);

@@ -87,6 +87,8 @@ __device__ __forceinline__ double shfl_xor_T(double v, int o) { return __shfl_xo
 __device__ __forceinline__ cplx shfl_xor_T(cplx v, int o) {
     return cplx{__shfl_xor_sync(0xffffffffu, v.re, o), __shfl_xor_sync(0xffffffffu, v.im, o)};
 }
+// first row the pass for column k touches (row k-1 of the pending reflector), as a multiple of 2
+__device__ __forceinline__ int rb_k(int k) { return k > 0 ? ((k - 1) & ~1) : 0; }
 // NaN norms must still be selectable as pivots (otherwise the column would never retire)
 __device__ __forceinline__ double nan_as_inf(double v) { return (v == v) ? v : INFINITY; }
 
@@ -96,6 +98,33 @@ template <typename T, int G> __device__ __forceinline__ void warp_sum_group(T (&
 #pragma unroll
         for (int u = 0; u < G; ++u) a[u] = a[u] + shfl_xor_T(a[u], o);
     }
+}
+// Sum G (= 2 or 4) per-lane values over the warp with G-fold fewer shuffles: afterwards every lane of
+// lane-group u (32/G consecutive lanes) holds the total of value u.
+template <typename T, int G> __device__ __forceinline__ T warp_sum_transposed(const T (&a)[G], int lane) {
+    static_assert(G == 2 || G == 4, "G must be 2 or 4");
+    T kk;
+    if constexpr (G == 4) {
+        const bool hi16 = lane & 16;
+        T s0 = hi16 ? a[0] : a[2], s1 = hi16 ? a[1] : a[3];
+        T k0 = hi16 ? a[2] : a[0], k1 = hi16 ? a[3] : a[1];
+        k0 = k0 + shfl_xor_T(s0, 16);
+        k1 = k1 + shfl_xor_T(s1, 16);
+        const bool hi8 = lane & 8;
+        T s = hi8 ? k0 : k1;
+        kk = hi8 ? k1 : k0;
+        kk = kk + shfl_xor_T(s, 8);
+    } else {
+        const bool hi16 = lane & 16;
+        T s = hi16 ? a[0] : a[1];
+        kk = hi16 ? a[1] : a[0];
+        kk = kk + shfl_xor_T(s, 16);
+        kk = kk + shfl_xor_T(kk, 8);
+    }
+    kk = kk + shfl_xor_T(kk, 4);
+    kk = kk + shfl_xor_T(kk, 2);
+    kk = kk + shfl_xor_T(kk, 1);
+    return kk;
 }
 template <typename T, int G> __device__ __forceinline__ T pick(const T (&a)[G], int u) {
     T r = a[0];
@@ -169,8 +198,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
         }
         acc = warp_sum(acc);
         if (lane == 0) {
-            double nr = sqrt(acc);
-            vn1[lc] = nr; vn2[lc] = nr;
+            vn1[lc] = acc; vn2[lc] = acc;   // SQUARED partial norms (no sqrt on the per-column critical path)
             pos[lc] = (c < n) ? -1 : n;   // padding columns count as already chosen
             wbuf[lc] = mk<T>(0.0); wbuf[nloc + lc] = mk<T>(0.0);
         }
@@ -180,26 +208,20 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
     __syncthreads();
     cluster_barrier<CS>();   // peers' candidate buffers are zeroed before anyone writes into them
 
-    // CTA-wide best active column -> (cand, cand_v); all threads get the result (2 barriers)
-    auto cta_candidate = [&](double bv, int bi, int& cand, double& cand_v) {
+    // After the pass: per-warp candidates go to shared memory, ONE block barrier, then warp 0 alone picks
+    // the CTA's candidate, builds the reflector that column would generate for position `kpos` (rows
+    // kpos..n-1; the pending reflector (vpend, wpend) is applied on the fly, the stored column is left
+    // untouched) and publishes it to every CTA.  The other warps go straight on to the cluster barrier.
+    auto select_and_publish = [&](double bv, int bi, int kpos, const T* vpend, const T* wpend, bool pending) {
         if (lane == 0) { redv[warp] = bv; redi[warp] = bi; }
         __syncthreads();
-        if (warp == 0) {
-            double v = (lane < CTA_WARPS) ? redv[lane] : -2.0;
-            int i = (lane < CTA_WARPS) ? redi[lane] : 0x7fffffff;
-            warp_argmax(v, i);
-            if (lane == 0) { redv[32] = v; redi[32] = i; }
-        }
-        __syncthreads();
-        cand_v = redv[32]; cand = redi[32];
-    };
-
-    // Build the reflector the local candidate column would generate for position `kpos` (rows kpos..n-1),
-    // with the pending reflector (vpend, wpend) applied on the fly, and publish it to every CTA.
-    auto publish_candidate = [&](int kpos, int cand, double cand_v, const T* vpend, const T* wpend, bool pending) {
+        if (warp != 0) return;
+        double cand_v = (lane < CTA_WARPS) ? redv[lane] : -2.0;
+        int cand = (lane < CTA_WARPS) ? redi[lane] : 0x7fffffff;
+        warp_argmax(cand_v, cand);
         const int par = kpos & 1;
         if (cand >= n) {   // no active column left in this CTA
-            if (tid < CS) peer<CS>(meta, tid)[par * 8 + rank].val = -1.0;
+            if (lane < CS) peer<CS>(meta, lane)[par * 8 + rank].val = -1.0;
             return;
         }
         const int lcs = cand / CS;
@@ -208,22 +230,23 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
         // rows [rz, kpos) are written as zeros: the pass for column kpos starts reading v at the (aligned)
         // first row of the PENDING reflector, kpos-1, and the slot still holds an older vector there
         const int rz = (kpos >= 2 ? kpos - 2 : 0) & ~(EPV - 1);
+        const int t_lo = rz >> 5;
         double ss = 0.0;
-        T xmine[(32 * RPLQ + CTA_THREADS - 1) / CTA_THREADS];
+        T alpha = mk<T>(0.0);
+        T x[RPLQ];
 #pragma unroll
-        for (int t = 0; t < (32 * RPLQ + CTA_THREADS - 1) / CTA_THREADS; ++t) {
-            const int r = rz + tid + t * CTA_THREADS;
-            T x = mk<T>(0.0);
-            if (r < n && r >= kpos) {
-                x = col[r];
-                if (pending) fms(x, vpend[r], wp);
-                if (r > kpos) ss += abs2_(x);
-                else redv[40] = real_(x), redv[41] = imag_(x);   // alpha
+        for (int t = 0; t < RPLQ; ++t) {
+            const int r = lane + 32 * t;
+            x[t] = mk<T>(0.0);
+            if (t >= t_lo && r < n && r >= kpos) {
+                T xv = col[r];
+                if (pending) fms(xv, vpend[r], wp);
+                if (r > kpos) ss += abs2_(xv); else alpha = xv;
+                x[t] = xv;
             }
-            xmine[t] = x;
         }
-        const double xnorm2 = block_sum(ss, redv);
-        const T alpha = mk<T>(redv[40], redv[41]);
+        const double xnorm2 = warp_sum(ss);
+        alpha = warp_sum(alpha);   // exactly one lane holds a non-zero alpha
         T tau, scal; double beta;
         if (xnorm2 == 0.0 && imag_(alpha) == 0.0) {
             tau = mk<T>(0.0); scal = mk<T>(0.0); beta = real_(alpha);
@@ -234,39 +257,49 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
         }
         T* slot = vcand + ((size_t)par * CS + rank) * vlen;
 #pragma unroll
-        for (int t = 0; t < (32 * RPLQ + CTA_THREADS - 1) / CTA_THREADS; ++t) {
-            const int r = rz + tid + t * CTA_THREADS;
-            if (r < n) {
+        for (int t = 0; t < RPLQ; ++t) {
+            const int r = lane + 32 * t;
+            if (t >= t_lo && r < n && r >= rz) {
                 T v = mk<T>(0.0);
-                if (r > kpos) v = xmine[t] * scal;
+                if (r > kpos) v = x[t] * scal;
                 else if (r == kpos) v = mk<T>(1.0);
 #pragma unroll
                 for (int q = 0; q < CS; ++q) peer<CS>(slot, q)[r] = v;
             }
         }
-        if (tid < CS) {
+        if (lane < CS) {
             CandMeta<T> m;
             m.val = cand_v; m.beta = beta; m.tau = tau; m.idx = cand; m.pad = 0;
-            peer<CS>(meta, tid)[par * 8 + rank] = m;
+            peer<CS>(meta, lane)[par * 8 + rank] = m;
         }
     };
 
     // ------------------------------------------------------------------ prologue: candidates for position 0
-    int cand; double cand_v;
     {
         double bv = -1.0; int bi = 0x7fffffff;
         for (int lc = tid; lc < nloc; lc += CTA_THREADS)
             if (pos[lc] < 0) { double v = nan_as_inf(vn1[lc]); int c = lc * CS + rank; if (v > bv || (v == bv && c < bi)) { bv = v; bi = c; } }
         warp_argmax(bv, bi);
-        cta_candidate(bv, bi, cand, cand_v);
-        publish_candidate(0, cand, cand_v, vloc, wbuf, false);
+        select_and_publish(bv, bi, 0, vloc, wbuf, false);
     }
 
     // ------------------------------------------------------------------ pivoted Householder QR
+    // per-phase cycle counters of cluster 0 (diagnostics; compiled in only with -DSLA_LDR_PROFILE,
+    // see profiles/ldr_phase_cycles.py)
+#ifdef SLA_LDR_PROFILE
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool prof = (p.prof != nullptr) && (blockIdx.x < CS);
+    long long tq = prof ? clock64() : 0;
+#define PROF_MARK(i) do { if (prof) { long long t_ = clock64(); pt[i] += t_ - tq; tq = t_; } } while (0)
+#else
+#define PROF_MARK(i) do { } while (0)
+#endif
     for (int k = 0; k < n; ++k) {
         const int par = k & 1;
         if (tid == 0) bulk_wait_read();   // the TMA has finished reading the candidate slot it was given
+        PROF_MARK(0);                      // tail of the previous iteration (publish for warp 0, nothing for others)
         cluster_barrier<CS>();            // the ONLY cluster-wide synchronisation per column
+        PROF_MARK(1);                      // cluster barrier (arrive + wait)
         // ---- winner of the CS candidates (identical decision in every CTA)
         int win = 0;
         {
@@ -303,7 +336,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
             }
         }
         if (k == n - 1) break;
-        __syncthreads();   // pos[] update visible before the pass
+        PROF_MARK(2);                      // winner pick, finalisation, TMA issue
+        // private copy of v_k: it is the "pending" reflector during the next pass
+        for (int r = (rb_k(k) & ~31) + tid; r < n; r += CTA_THREADS) vsave[r] = vcur[r];
         // ---- fused pass: apply pending H_{k-1}, accumulate v_k^H a, down-date norms, local candidate
         const T tauc = conj_(tauk);
         const int rb = (k > 0) ? ((k - 1) & ~(EPV - 1)) : 0;
@@ -316,13 +351,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
 #pragma unroll
             for (int u = 0; u < CPW; ++u) {
                 const int lc = g0 + u * CTA_WARPS;
-                act[u] = (lc < nloc) && (pos[lc] < 0);
+                // pos[] of the column that just won is being written concurrently: exclude it explicitly
+                act[u] = (lc < nloc) && (pos[lc] < 0) && !(rank == win && lc == plc);
                 wp[u] = act[u] ? wprev[lc] : mk<T>(0.0);
                 acc[u] = mk<T>(0.0);
                 any |= act[u];
-            }
-            if (g0 == warp) {   // one warp-wide copy of v_k into the private buffer (for the next pass)
-                for (int r = rb + lane; r < n; r += 32) if (warp == (r >> 5) % CTA_WARPS) vsave[r] = vcur[r];
             }
             if (!any) continue;
             if constexpr (!CP) {
@@ -357,35 +390,36 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
                     }
                 }
             }
-            warp_sum_group<T, CPW>(acc);
+            const T mysum = warp_sum_transposed<T, CPW>(acc, lane);
             __syncwarp();
-            // lane u (< CPW) finishes column u: w, pivot-row entry, norm down-date
+            // the first lane of lane-group u finishes column u: w, pivot-row entry, norm down-date (squared)
+            constexpr int FLS = 32 / CPW;
             bool flagged = false;
             double v1 = -1.0;
             int myc = 0x7fffffff;
             T wnew = mk<T>(0.0);
-            const int mylc = g0 + lane * CTA_WARPS;
-            const bool mine = (lane < CPW) && (mylc < nloc) && (pos[mylc] < 0);
+            const int myu = lane / FLS;
+            const int mylc = g0 + myu * CTA_WARPS;
+            const bool mine = ((lane % FLS) == 0) && (mylc < nloc) && (pos[mylc] < 0) && !(rank == win && mylc == plc);
             if (mine) {
-                wnew = tauc * pick<T, CPW>(acc, lane);
+                wnew = tauc * mysum;
                 wcur[mylc] = wnew;
                 myc = mylc * CS + rank;
                 v1 = vn1[mylc];
                 if (v1 != 0.0) {
                     const T ak = A[(size_t)mylc * ldc + k] - wnew;   // a'(k,c): v_k(k) = 1
-                    double temp = abs_(ak) / v1;
-                    temp = fmax(0.0, (1.0 + temp) * (1.0 - temp));
-                    const double q = v1 / vn2[mylc];
-                    if (temp * q * q <= TOL3Z_C) flagged = true;
-                    else { v1 *= sqrt(temp); vn1[mylc] = v1; }
+                    const double temp = fmax(0.0, 1.0 - abs2_(ak) / v1);
+                    const double q2 = v1 / vn2[mylc];
+                    if (temp * q2 <= TOL3Z_C) flagged = true;
+                    else { v1 *= temp; vn1[mylc] = v1; }
                 }
             }
             unsigned fl = __ballot_sync(0xffffffffu, flagged);
             while (fl) {   // exact norm of a flagged column below row k (new reflector applied on the fly)
-                const int u = __ffs(fl) - 1;
+                const int src = __ffs(fl) - 1;
                 fl &= fl - 1;
-                const int lc = g0 + u * CTA_WARPS;
-                const T wsel = mk<T>(__shfl_sync(0xffffffffu, real_(wnew), u), __shfl_sync(0xffffffffu, imag_(wnew), u));
+                const int lc = g0 + (src / FLS) * CTA_WARPS;
+                const T wsel = mk<T>(__shfl_sync(0xffffffffu, real_(wnew), src), __shfl_sync(0xffffffffu, imag_(wnew), src));
                 const T* col = A + (size_t)lc * ldc;
                 double ss = 0.0;
                 for (int r = k + 1 + lane; r < n; r += 32) {
@@ -394,7 +428,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
                     ss += abs2_(x);
                 }
                 ss = warp_sum(ss);
-                if (lane == u) { v1 = sqrt(ss); vn1[lc] = v1; vn2[lc] = v1; }
+                if (lane == src) { v1 = ss; vn1[lc] = ss; vn2[lc] = ss; }
             }
             if (mine) {
                 v1 = nan_as_inf(v1);
@@ -402,10 +436,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
             }
         }
         warp_argmax(bv, bi);
-        cta_candidate(bv, bi, cand, cand_v);
+        PROF_MARK(3);                      // fused pass + finish + warp argmax
         // ---- speculative reflector for position k+1 from the local candidate (pending = H_k)
-        publish_candidate(k + 1, cand, cand_v, vcur, wcur, true);
+        select_and_publish(bv, bi, k + 1, vcur, wcur, true);
     }
+    PROF_MARK(4);
     if (tid == 0) bulk_wait_all();   // all reflectors have landed in global memory
     __syncthreads();
 
@@ -435,6 +470,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
     }
     __threadfence();
     cluster_barrier<CS>();   // every CTA's reflectors are in global memory and visible
+    PROF_MARK(5);              // extraction of d, R + identity init + barrier
 
     {
         T* const ring = vcand;   // [2][QKC][ldc], aliases the candidate buffers (no longer needed)
@@ -521,6 +557,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
             __syncthreads();
         }
     }
+    PROF_MARK(6);              // Q phase
     cluster_barrier<CS>();   // every CTA is done reading reflectors from Lg before anyone overwrites them
     for (int lc = warp; lc < nloc; lc += CTA_WARPS) {
         const int c = lc * CS + rank;
@@ -529,6 +566,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
         T* dst = Lg + (long long)c * ldl;
         for (int r = lane; r < n; r += 32) dst[r] = col[r];
     }
+    PROF_MARK(7);
+#ifdef SLA_LDR_PROFILE
+    if (prof && (lane == 0) && (warp == 0 || warp == 1)) {
+        // [rank][warp0/warp1][8 phases]
+        for (int i = 0; i < 8; ++i) p.prof[(rank * 2 + warp) * 8 + i] = pt[i];
+    }
+#endif
+#undef PROF_MARK
 }
 
 // smallest cluster size whose CTAs can hold the matrix (0: does not fit / n too large for the register tile)
