@@ -216,7 +216,8 @@ def run_gpu(args):
     cfg = get_cfg(args.config, args.chains)
     n, L, chains = cfg.N, cfg.L, cfg.chains
     dt = torch.complex128 if cfg.dtype.kind == "c" else torch.float64
-    chain_ids = range(rank * chains, (rank + 1) * chains)      # global chain ids: sharding-invariant fields
+    from sla_b200 import walkers
+    chain_ids = walkers.weak_chain_ids(chains, rank)           # global chain ids: sharding-invariant fields
 
     expK_h = torch.from_numpy(np.ascontiguousarray(cfg.expK().T)).pin_memory()      # column-major storage
     fields_h = torch.from_numpy(cfg.fields(chain_ids)).pin_memory()
@@ -234,13 +235,7 @@ def run_gpu(args):
 
     def reduce_walkers():
         # cross-walker reduction of log-determinants and signs (the only collective on this path)
-        acc[0] = logdet.sum()
-        s = sign.sum()
-        acc[1] = s.real if dt == torch.complex128 else s
-        acc[2] = s.imag if dt == torch.complex128 else 0.0
-        acc[3] = float(chains)
-        if world > 1:
-            dist.all_reduce(acc)
+        walkers.reduce_walkers(logdet, sign, out=acc)
 
     def step_device():
         sla.greens_chain(expK_d, fields_d, cfg.lam, cfg.n_stab, cfg.inverse, G=G, logdet=logdet, sign=sign, ws=ws)
