@@ -37,6 +37,7 @@ constexpr int NSCAL = 8;  // per-matrix scalar slots in a workspace
 // Workspace blob = LDRWorkspace (src/LDR.jl:51-70): M, M', M'' plus the LU/QR scratch and scalars.
 template <typename T> struct Ws {
     T *M, *Mp, *Mpp, *X, *Tw;
+    double *v1, *v2;  // n * batch each: prepared scaling multipliers (the reference's ws.v)
     double* sc;  // NSCAL * batch
     T* st;       // NSCAL * batch
     int* info;   // batch
@@ -45,6 +46,7 @@ template <typename T> struct Ws {
         size_t nn = (size_t)n * n * batch * sizeof(T);
         size_t b = 4 * align_up(nn);
         b += align_up(ldr_twork_elems<T>(n) * (size_t)batch * sizeof(T));
+        b += 2 * align_up((size_t)n * batch * sizeof(double));
         b += align_up((size_t)NSCAL * batch * sizeof(double));
         b += align_up((size_t)NSCAL * batch * sizeof(T));
         b += align_up((size_t)batch * sizeof(int));
@@ -59,6 +61,8 @@ template <typename T> struct Ws {
         X = (T*)p; p += nn;
         tw_elems = ldr_twork_elems<T>(n);
         Tw = (T*)p; p += align_up(tw_elems * (size_t)batch * sizeof(T));
+        v1 = (double*)p; p += align_up((size_t)n * batch * sizeof(double));
+        v2 = (double*)p; p += align_up((size_t)n * batch * sizeof(double));
         sc = (double*)p; p += align_up((size_t)NSCAL * batch * sizeof(double));
         st = (T*)p; p += align_up((size_t)NSCAL * batch * sizeof(T));
         info = (int*)p;
@@ -86,13 +90,22 @@ template <typename T> struct Ctx {
     int gemm(T* C, int opa, const T* A, long long sA, int opb, const T* B, long long sB, const double* rs = nullptr,
              int rs_mode = SCALE_NONE, const double* cs = nullptr, int cs_mode = SCALE_NONE, int accumulate = 0,
              long long sC = -1) const {
+        // the epilogue only multiplies: turn D^-1 / min(D,1) / 1/max(D,1) into multiplier vectors first
+        if (rs && rs_mode != SCALE_MUL) {
+            CK(scale_prep_batched(w.v1, rs, rs_mode, (long long)n * batch, s));
+            rs = w.v1;
+        }
+        if (cs && cs_mode != SCALE_MUL) {
+            CK(scale_prep_batched(w.v2, cs, cs_mode, (long long)n * batch, s));
+            cs = w.v2;
+        }
         GemmArgs<T> g{};
         g.A = A; g.B = B; g.C = C;
         g.strideA = sA; g.strideB = sB; g.strideC = (sC < 0) ? nn : sC;
         g.lda = g.ldb = g.ldc = n;
         g.M = g.N = g.K = n;
-        g.rs = rs; g.stride_rs = n; g.rs_mode = rs_mode; g.rs_div = 0; g.stride_rs_hi = 0;
-        g.cs = cs; g.stride_cs = n; g.cs_mode = cs_mode;
+        g.rs = rs; g.stride_rs = n; g.rs_mode = SCALE_MUL; g.rs_div = 0; g.stride_rs_hi = 0;
+        g.cs = cs; g.stride_cs = n; g.cs_mode = SCALE_MUL;
         g.accumulate = accumulate;
         g.batch = batch;
         CK(gemm_batched<T>(opa, opb, g, s));

@@ -28,6 +28,8 @@ template <typename T> struct GemmArgs {
     long long strideA, strideB, strideC;  // in elements; 0 = operand shared by the whole batch
     int lda, ldb, ldc;
     int M, N, K;
+    // row / column scaling vectors are plain MULTIPLIERS (the D, D^-1, min(D,1), 1/max(D,1) factors are
+    // prepared by scale_prep_batched); rs_mode / cs_mode are ignored by the kernel
     const double* rs; long long stride_rs; int rs_mode;   // row scaling (length M), may be null
     int rs_div; long long stride_rs_hi;                    // rs_div>0: rs offset = (b/rs_div)*stride_rs_hi + (b%rs_div)*stride_rs
     const double* cs; long long stride_cs; int cs_mode;   // column scaling (length N), may be null
@@ -47,9 +49,9 @@ template <typename T, bool IDXC, int BIDX, int BK> struct OperandTile {
     static constexpr int EPC = 16 / (int)sizeof(T);  // elements per 16-byte chunk
 
     // global element (idx, k) lives at g[idx*sidx + k*sk] with exactly one of sidx/sk == 1
-    template <int NT>
+    template <int NT, bool VEC>
     __device__ static __forceinline__ void load(T* s, const T* g, int ld, int idx0, int k0, int idx_max,
-                                                int k_max, bool vec_ok, int tid) {
+                                                int k_max, int tid) {
         if (IDXC) {
             constexpr int CPR = BIDX / EPC;  // chunks per k-row
             constexpr int TOTAL = CPR * BK;
@@ -59,7 +61,7 @@ template <typename T, bool IDXC, int BIDX, int BK> struct OperandTile {
                 int gi = idx0 + ii, gk = k0 + kk;
                 const T* src = g + (long long)gk * ld + gi;
                 int nvalid = (gk < k_max) ? max(0, min(EPC, idx_max - gi)) : 0;
-                copy_chunk(dst, src, nvalid, vec_ok, g);
+                copy_chunk<VEC>(dst, src, nvalid, g);
             }
         } else {
             constexpr int CPR = BK / EPC;  // chunks per idx-row
@@ -70,13 +72,13 @@ template <typename T, bool IDXC, int BIDX, int BK> struct OperandTile {
                 int gi = idx0 + ii, gk = k0 + kk;
                 const T* src = g + (long long)gi * ld + gk;
                 int nvalid = (gi < idx_max) ? max(0, min(EPC, k_max - gk)) : 0;
-                copy_chunk(dst, src, nvalid, vec_ok, g);
+                copy_chunk<VEC>(dst, src, nvalid, g);
             }
         }
     }
-    __device__ static __forceinline__ void copy_chunk(T* dst, const T* src, int nvalid, bool vec_ok,
-                                                      const T* safe) {
-        if (vec_ok || EPC == 1) {
+    template <bool VEC>
+    __device__ static __forceinline__ void copy_chunk(T* dst, const T* src, int nvalid, const T* safe) {
+        if constexpr (VEC || EPC == 1) {
             cp_async16(dst, nvalid > 0 ? (const void*)src : (const void*)safe, nvalid * (int)sizeof(T));
         } else {  // real data whose rows are only 8-byte aligned (odd ld): two 8-byte copies
             cp_async8(dst, nvalid > 0 ? (const void*)src : (const void*)safe, nvalid > 0 ? 8 : 0);
@@ -99,7 +101,7 @@ __device__ __forceinline__ void mma_tile(cplx (&acc)[2], cplx nf, cplx mf) {
     dmma884(acc[0].im, acc[1].im, nf.im, mf.re);
 }
 
-template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES>
+template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES, bool VEC>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(GemmArgs<T> p) {
     constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
     constexpr int NT = WARPS_M * WARPS_N * 32;
@@ -124,8 +126,6 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(Gem
     const T* A = p.A + (long long)b * p.strideA;
     const T* B = p.B + (long long)b * p.strideB;
     T* C = p.C + (long long)b * p.strideC;
-    const bool vecA = ((p.lda & 1) == 0) && ((((uintptr_t)A) & 15) == 0);
-    const bool vecB = ((p.ldb & 1) == 0) && ((((uintptr_t)B) & 15) == 0);
 
     T acc[NF][MF][2];
 #pragma unroll
@@ -137,8 +137,8 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(Gem
     auto load_stage = [&](int stage, int kt) {
         T* sa = smem + stage * STAGE_ELEMS;
         T* sb = sa + TileA::ELEMS;
-        TileA::template load<NT>(sa, A, p.lda, m0, kt * BK, p.M, p.K, vecA, tid);
-        TileB::template load<NT>(sb, B, p.ldb, n0, kt * BK, p.N, p.K, vecB, tid);
+        TileA::template load<NT, VEC>(sa, A, p.lda, m0, kt * BK, p.M, p.K, tid);
+        TileB::template load<NT, VEC>(sb, B, p.ldb, n0, kt * BK, p.N, p.K, tid);
     };
 
 #pragma unroll
@@ -158,23 +158,29 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(Gem
         }
         const T* sa = smem + (kt % STAGES) * STAGE_ELEMS;
         const T* sb = sa + TileA::ELEMS;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            T nf[NF], mf[MF];
+        // register double buffering of the fragments: the LDS of step kk+4 are issued before the DMMAs of kk
+        T nf[2][NF], mf[2][MF];
+        auto load_frags = [&](int buf, int kk) {
 #pragma unroll
             for (int i = 0; i < NF; ++i) {
                 T v = TileB::frag(sb, wn * WN + i * 8 + fi, kk + fk);
-                nf[i] = (OPB == OP_C) ? conj_(v) : v;
+                nf[buf][i] = (OPB == OP_C) ? conj_(v) : v;
             }
 #pragma unroll
             for (int j = 0; j < MF; ++j) {
                 T v = TileA::frag(sa, wm * WM + j * 8 + fi, kk + fk);
-                mf[j] = (OPA == OP_C) ? conj_(v) : v;
+                mf[buf][j] = (OPA == OP_C) ? conj_(v) : v;
             }
+        };
+        load_frags(0, 0);
+#pragma unroll
+        for (int kk = 0; kk < BK; kk += 4) {
+            const int cur = (kk >> 2) & 1;
+            if (kk + 4 < BK) load_frags(cur ^ 1, kk + 4);
 #pragma unroll
             for (int i = 0; i < NF; ++i)
 #pragma unroll
-                for (int j = 0; j < MF; ++j) mma_tile(acc[i][j], nf[i], mf[j]);
+                for (int j = 0; j < MF; ++j) mma_tile(acc[i][j], nf[cur][i], mf[cur][j]);
         }
     }
     cp_async_wait<0>();
@@ -198,12 +204,12 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(Gem
             T v0 = acc[i][j][0], v1 = acc[i][j][1];
             const bool has1 = (m + 1 < p.M);
             if (rs) {
-                v0 = apply_scale(v0, rs[m], p.rs_mode);
-                if (has1) v1 = apply_scale(v1, rs[m + 1], p.rs_mode);
+                v0 = v0 * rs[m];
+                if (has1) v1 = v1 * rs[m + 1];
             }
             if (cs) {
-                v0 = apply_scale(v0, csv, p.cs_mode);
-                v1 = apply_scale(v1, csv, p.cs_mode);
+                v0 = v0 * csv;
+                v1 = v1 * csv;
             }
             bool done = false;
             if constexpr (sizeof(T) == 8) {
@@ -230,13 +236,13 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(Gem
     }
 }
 
-template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES>
-static cudaError_t launch_gemm_cfg(const GemmArgs<T>& p, cudaStream_t stream) {
+template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES, bool VEC>
+static cudaError_t launch_gemm_vec(const GemmArgs<T>& p, cudaStream_t stream) {
     using TileA = OperandTile<T, OPA == OP_N, BM, BK>;
     using TileB = OperandTile<T, OPB == OP_C, BN, BK>;
     constexpr int SMEM = STAGES * (TileA::ELEMS + TileB::ELEMS) * (int)sizeof(T);
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
-    auto kern = gemm_kernel<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES>;
+    auto kern = gemm_kernel<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES, VEC>;
     static bool configured = false;  // per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -248,6 +254,17 @@ static cudaError_t launch_gemm_cfg(const GemmArgs<T>& p, cudaStream_t stream) {
     kern<<<(unsigned)((long long)tiles * p.batch), NT, SMEM, stream>>>(p);
     ++g_launch_count;
     return cudaGetLastError();
+}
+
+// 16-byte cp.async needs even leading dimensions/strides and 16-byte aligned bases (always true for complex)
+template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES>
+static cudaError_t launch_gemm_cfg(const GemmArgs<T>& p, cudaStream_t stream) {
+    bool vec = true;
+    if (sizeof(T) == 8)
+        vec = ((p.lda & 1) == 0) && ((p.ldb & 1) == 0) && ((p.strideA & 1) == 0) && ((p.strideB & 1) == 0) &&
+              ((((uintptr_t)p.A) & 15) == 0) && ((((uintptr_t)p.B) & 15) == 0);
+    if (vec) return launch_gemm_vec<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES, true>(p, stream);
+    return launch_gemm_vec<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES, false>(p, stream);
 }
 
 }  // namespace sla

@@ -56,6 +56,8 @@ template <typename T> struct CombineArgs {
     double* logdet; T* sign; int batch;
 };
 template <typename T> cudaError_t combine_batched(const CombineArgs<T>& a, cudaStream_t s);
+// out[i] = multiplier realising ScaleMode `mode` with d[i] (feeds the GEMM epilogue, which only multiplies)
+cudaError_t scale_prep_batched(double* out, const double* d, int mode, long long count, cudaStream_t s);
 // ev[c,l,i] = exp(lam * s[c,l,i])
 cudaError_t hs_exp_batched(double* ev, const signed char* fields, double lam, long long count, cudaStream_t s);
 

@@ -118,6 +118,23 @@ template <typename T> __global__ void combine_kernel(CombineArgs<T> a) {
     if (a.sign) a.sign[b] = s;
 }
 
+// out[i] = the MULTIPLIER that realises ScaleMode `mode` with d[i]
+__global__ void scale_prep_kernel(double* out, const double* d, int mode, long long count) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const double v = d[i];
+    double r = v;
+    switch (mode) {
+        case SCALE_DIV: r = 1.0 / v; break;
+        case SCALE_MUL_MIN1: r = fmin(v, 1.0); break;
+        case SCALE_DIV_MAX1: r = 1.0 / fmax(v, 1.0); break;
+        case SCALE_MUL_MAX1: r = fmax(v, 1.0); break;
+        case SCALE_DIV_MIN1: r = 1.0 / fmin(v, 1.0); break;
+        default: break;
+    }
+    out[i] = r;
+}
+
 __global__ void hs_exp_kernel(double* ev, const signed char* f, double ep, double em, long long count) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) ev[i] = f[i] > 0 ? ep : em;
@@ -186,6 +203,13 @@ cudaError_t logsum_batched(double* out, const double* d, long long sd, int mode,
 template <typename T> cudaError_t combine_batched(const CombineArgs<T>& a, cudaStream_t s) {
     if (a.batch <= 0) return cudaSuccess;
     combine_kernel<T><<<(a.batch + 127) / 128, 128, 0, s>>>(a);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+
+cudaError_t scale_prep_batched(double* out, const double* d, int mode, long long count, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    scale_prep_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(out, d, mode, count);
     ++g_launch_count;
     return cudaGetLastError();
 }
