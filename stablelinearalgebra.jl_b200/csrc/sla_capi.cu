@@ -122,9 +122,17 @@ template <typename T> struct Ctx {
         a.jpvt_out = nullptr;
         a.prof = g_ldr_prof;
         a.n = n; a.batch = batch;
-        // on-chip cluster kernel when the matrix fits the shared memory of <= 8 CTAs, else the L2-streaming one
-        static const bool force_v1 = getenv("SLA_LDR_STREAMING") != nullptr;
-        if (!force_v1 && ldr_cluster_size<T>(n) > 0) CK(ldr_cluster_batched<T>(a, s));
+        // register-resident cluster kernel (n <= 256), else the shared-memory cluster kernel (matrix fits the
+        // shared memory of <= 8 CTAs), else the L2-streaming kernel.  SLA_LDR_ALGO=reg|cluster|streaming forces one.
+        static const int forced = [] {
+            const char* e = getenv("SLA_LDR_ALGO");
+            if (getenv("SLA_LDR_STREAMING")) return 3;
+            if (!e) return 0;
+            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : 0));
+        }();
+        const bool can_reg = ldr_reg_cluster_size<T>(n) > 0, can_cl = ldr_cluster_size<T>(n) > 0;
+        if ((forced == 0 || forced == 1) && can_reg) CK(ldr_reg_batched<T>(a, s));
+        else if ((forced == 0 || forced == 1 || forced == 2) && can_cl) CK(ldr_cluster_batched<T>(a, s));
         else CK(ldr_batched<T>(a, s));
         return 0;
     }

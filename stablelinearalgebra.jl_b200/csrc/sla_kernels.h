@@ -22,6 +22,9 @@ template <typename T> size_t ldr_twork_elems(int n);
 // on-chip (thread-block cluster + DSMEM) version, sla_ldr_cluster.cu; cluster size 0 = matrix too large
 template <typename T> cudaError_t ldr_cluster_batched(const LdrArgs<T>& p, cudaStream_t s);
 template <typename T> int ldr_cluster_size(int n);
+// register-resident cluster version for n <= 256, sla_ldr_reg.cu; cluster size 0 = not supported
+template <typename T> cudaError_t ldr_reg_batched(const LdrArgs<T>& p, cudaStream_t s);
+template <typename T> int ldr_reg_cluster_size(int n);
 
 // ---- LU / inverse with log|det| and sign (sla_lu.cu) ----------------------------------------
 template <typename T> struct LuArgs {

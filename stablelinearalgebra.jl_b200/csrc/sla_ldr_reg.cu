@@ -1,0 +1,521 @@
+// Batched LDR factorisation, register-resident version: one thread-block cluster owns one matrix and the
+// matrix lives in the REGISTER FILES of its CTAs for the whole factorisation.
+//
+// Replaces `ldr!(F, ws)` (src/LDR.jl:160-188: geqp3! + triu/abs/ldiv!/mul_P! + orgqr!) for n <= 256.
+// Same mathematics and same cluster protocol as sla_ldr_cluster.cu (speculative pivot candidates pushed
+// into the peers' shared memory, one cluster barrier per column, no physical column swaps, squared-norm
+// down-dating with LAPACK's cancellation safeguard, TMA store of the reflectors), but:
+//   * a warp owns CPW columns (column-cyclic over CTAs, then over warps) and keeps them as a
+//     CPW x RPL register tile per lane (row r = lane + 32 t): the per-column pass is pure register math --
+//     RPL shared-memory loads for v_k, a dot product per column, a transposed warp reduction, an EAGER
+//     rank-1 update -- with no shared-memory traffic for the matrix at all;
+//   * only the warp that holds the CTA's best column builds the candidate reflector (straight from its
+//     registers) and pushes it to the peers, so the serial FP64 sqrt/div chain is issued once per CTA;
+//   * retired columns (= columns of R') are parked in shared memory and scaled/written at the end;
+//   * Q = H_0...H_{n-1} is formed with the same register tiles: the reflectors stream back through a
+//     cp.async ring and each warp applies them to its columns of the identity, never leaving registers.
+#include <cooperative_groups.h>
+
+#include "sla_cta.cuh"
+#include "sla_kernels.h"
+
+namespace cg = cooperative_groups;
+
+namespace sla {
+
+namespace {
+
+constexpr double TOL3Z_R = 1.4901161193847656e-08;  // sqrt(eps), LAPACK ?laqps / ?laqp2
+constexpr int QKC_R = 8;                             // reflectors per chunk in the Q phase
+
+template <typename T> struct RMeta {
+    double val;   // squared down-dated norm (-1: no active column left)
+    double beta;
+    T tau;
+    int idx;
+    int pad;
+};
+
+template <typename T, int RPL, int CPW> struct RegLayout {
+    static constexpr int NMAX = 32 * RPL;
+    static constexpr int VLEN = NMAX + 8;
+    size_t offCand, offRst, offTau, offMeta, offD, offWval, offWidx, total;
+    __host__ __device__ RegLayout(int n, int cs) {
+        size_t o = 0;
+        // candidate reflectors [2][cs][VLEN]; the Q-phase ring [2][QKC][NMAX] aliases this region
+        size_t cand = 2 * (size_t)cs * VLEN * sizeof(T), ring = 2 * (size_t)QKC_R * NMAX * sizeof(T);
+        offCand = o; o += (cand > ring ? cand : ring);
+        offRst = o; o += (size_t)CTA_WARPS * CPW * n * sizeof(T);   // parked R' columns [lc][n]
+        offTau = o; o += (size_t)n * sizeof(T);
+        offMeta = o; o += 2 * 8 * sizeof(RMeta<T>);
+        o = (o + 15) & ~(size_t)15;
+        offD = o; o += (size_t)n * sizeof(double);
+        offWval = o; o += 32 * sizeof(double);
+        offWidx = o; o += 32 * sizeof(int);
+        total = o + 64;
+    }
+};
+
+template <int CS> __device__ __forceinline__ void cl_barrier() {
+    if constexpr (CS == 1) __syncthreads();
+    else cg::this_cluster().sync();
+}
+template <int CS, typename P> __device__ __forceinline__ P* cl_peer(P* local, int rank) {
+    if constexpr (CS == 1) return local;
+    else return cg::this_cluster().map_shared_rank(local, rank);
+}
+
+__device__ __forceinline__ double shx(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ cplx shx(cplx v, int o) { return cplx{shx(v.re, o), shx(v.im, o)}; }
+__device__ __forceinline__ double shb(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
+__device__ __forceinline__ cplx shb(cplx v, int l) { return cplx{shb(v.re, l), shb(v.im, l)}; }
+__device__ __forceinline__ double nan_inf(double v) { return (v == v) ? v : INFINITY; }
+
+// Sum G (power of two, <= 8) per-lane values over the warp with far fewer shuffles than G butterflies:
+// each round halves the number of values a lane carries.  Afterwards every lane of lane-group u
+// (32/G consecutive lanes) holds the total of a[u].
+template <typename T, int G> __device__ __forceinline__ T reduce_transposed_inner(const T (&a)[G], int lane, int bit) {
+    if constexpr (G == 1) {
+        T v = a[0];
+        for (int o = bit; o > 0; o >>= 1) v = v + shx(v, o);
+        return v;
+    } else {
+        constexpr int H = G / 2;
+        const bool hi = lane & bit;
+        T keep[H];
+#pragma unroll
+        for (int i = 0; i < H; ++i) {
+            T send = hi ? a[i] : a[i + H];
+            T mine = hi ? a[i + H] : a[i];
+            keep[i] = mine + shx(send, bit);
+        }
+        return reduce_transposed_inner<T, H>(keep, lane, bit >> 1);
+    }
+}
+template <typename T, int G> __device__ __forceinline__ T reduce_transposed(const T (&a)[G], int lane) {
+    return reduce_transposed_inner<T, G>(a, lane, 16);
+}
+
+template <typename T, int G> __device__ __forceinline__ T pickv(const T (&a)[G], int u) {
+    T r = a[0];
+#pragma unroll
+    for (int i = 1; i < G; ++i) if (u == i) r = a[i];
+    return r;
+}
+
+__device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, unsigned bytes) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+}  // namespace
+
+template <typename T, int CS, int RPL, int CPW>
+__global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
+    using Lay = RegLayout<T, RPL, CPW>;
+    constexpr int NMAX = Lay::NMAX, VLEN = Lay::VLEN;
+    constexpr int FLS = 32 / CPW;                 // lanes per lane-group; lane u*FLS leads column u of the warp
+    constexpr bool CP = is_cplx<T>::value;
+    constexpr int EPV = CP ? 1 : 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n;
+    const Lay lay(n, CS);
+    T* const vcand = reinterpret_cast<T*>(smem_raw + lay.offCand);        // [2][CS][VLEN]
+    T* const Rst = reinterpret_cast<T*>(smem_raw + lay.offRst);           // [16*CPW][n]
+    T* const taus = reinterpret_cast<T*>(smem_raw + lay.offTau);
+    RMeta<T>* const meta = reinterpret_cast<RMeta<T>*>(smem_raw + lay.offMeta);
+    double* const dvec = reinterpret_cast<double*>(smem_raw + lay.offD);
+    double* const wval = reinterpret_cast<double*>(smem_raw + lay.offWval);
+    int* const widx = reinterpret_cast<int*>(smem_raw + lay.offWidx);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int rank = 0;
+    if constexpr (CS > 1) rank = (int)cg::this_cluster().block_rank();
+    const int b = blockIdx.x / CS;
+    T* Lg = p.L + (long long)b * p.strideL;
+    const int ldl = p.ldl;
+    const T* Ain = p.Ain ? p.Ain + (long long)b * p.strideAin : Lg;
+    const int ldin = p.Ain ? p.ldain : ldl;
+    const bool bulk_ok = ((((uintptr_t)Lg) & 15) == 0) && (((size_t)ldl * sizeof(T)) % 16 == 0) && (CP || (n % 2 == 0));
+
+    // ------------------------------------------------------------------ load: columns -> registers
+    // column u of this warp: local index lc = warp + 16 u, global c = lc*CS + rank
+    T a[CPW][RPL];
+    unsigned active = 0;
+    double ssq[CPW];
+#pragma unroll
+    for (int u = 0; u < CPW; ++u) {
+        const int c = (warp + CTA_WARPS * u) * CS + rank;
+        ssq[u] = 0.0;
+        if (c < n) {
+            active |= 1u << u;
+            const T* src = Ain + (long long)c * ldin;
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                const int r = lane + 32 * t;
+                a[u][t] = (r < n) ? src[r] : mk<T>(0.0);
+                ssq[u] += abs2_(a[u][t]);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) a[u][t] = mk<T>(0.0);
+        }
+    }
+    // squared partial norms live in the lane-group leaders' registers
+    const int myu = lane / FLS;
+    const bool leader = (lane % FLS) == 0;
+    double vn1 = reduce_transposed<double, CPW>(ssq, lane), vn2 = vn1;
+    const int myc = (warp + CTA_WARPS * myu) * CS + rank;
+
+    for (int r = tid; r < 2 * CS * VLEN; r += CTA_THREADS) vcand[r] = mk<T>(0.0);
+    __syncthreads();
+    cl_barrier<CS>();   // peers' candidate buffers are zeroed before anyone writes into them (also: all inputs read)
+
+    // warp candidate -> shared; block barrier; the warp holding the CTA's best column builds the reflector
+    // for position kpos from its registers and pushes it (plus norm, index, tau, beta) to every CTA.
+    auto select_and_publish = [&](int kpos) {
+        double bv = -1.0; int bi = 0x7fffffff;
+        if (leader && ((active >> myu) & 1u)) { bv = nan_inf(vn1); bi = myc; }
+        warp_argmax(bv, bi);
+        if (lane == 0) { wval[warp] = bv; widx[warp] = bi; }
+        __syncthreads();
+        double cv = wval[0]; int ci = widx[0]; int cw = 0;
+#pragma unroll
+        for (int w = 1; w < CTA_WARPS; ++w) {
+            const double ov = wval[w]; const int oi = widx[w];
+            if (ov > cv || (ov == cv && oi < ci)) { cv = ov; ci = oi; cw = w; }
+        }
+        const int par = kpos & 1;
+        if (ci >= n) {   // no active column left in this CTA
+            if (warp == 0 && lane < CS) cl_peer<CS>(meta, lane)[par * 8 + rank].val = -1.0;
+            return;
+        }
+        if (warp != cw) return;
+        const int ub = (ci / CS) / CTA_WARPS;   // which of my columns
+        T x[RPL];
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) x[t] = a[0][t];
+#pragma unroll
+        for (int u = 1; u < CPW; ++u)
+            if (ub == u) {
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) x[t] = a[u][t];
+            }
+        double ss = 0.0;
+        T alpha = mk<T>(0.0);
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            const int r = lane + 32 * t;
+            if (r > kpos) ss += abs2_(x[t]);
+            else if (r == kpos) alpha = x[t];
+        }
+        const double xnorm2 = warp_sum(ss);
+        alpha = warp_sum(alpha);   // exactly one lane holds a non-zero alpha
+        T tau, scal; double beta;
+        if (xnorm2 == 0.0 && imag_(alpha) == 0.0) {
+            tau = mk<T>(0.0); scal = mk<T>(0.0); beta = real_(alpha);
+        } else {
+            beta = -copysign(sqrt(abs2_(alpha) + xnorm2), real_(alpha));
+            tau = mk<T>((beta - real_(alpha)) / beta, -imag_(alpha) / beta);
+            scal = mk<T>(1.0) / (alpha - mk<T>(beta));
+        }
+        // rows [rz, kpos) are written as zeros (the slot still holds an older vector there and the TMA /
+        // the pass read from an aligned start)
+        const int rz = (kpos >= 2 ? kpos - 2 : 0) & ~(EPV - 1);
+        T* slot = vcand + ((size_t)par * CS + rank) * VLEN;
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            const int r = lane + 32 * t;
+            if (r < n && r >= rz) {
+                T v = mk<T>(0.0);
+                if (r > kpos) v = x[t] * scal;
+                else if (r == kpos) v = mk<T>(1.0);
+#pragma unroll
+                for (int q = 0; q < CS; ++q) cl_peer<CS>(slot, q)[r] = v;
+            }
+        }
+        if (lane < CS) {
+            RMeta<T> m;
+            m.val = cv; m.beta = beta; m.tau = tau; m.idx = ci; m.pad = 0;
+            cl_peer<CS>(meta, lane)[par * 8 + rank] = m;
+        }
+    };
+
+    select_and_publish(0);
+
+    // ------------------------------------------------------------------ pivoted Householder QR
+    for (int k = 0; k < n; ++k) {
+        const int par = k & 1;
+        if (tid == 0) tma_wait_read();   // the TMA is done reading the slot it was given two columns ago
+        cl_barrier<CS>();                // the ONLY cluster-wide synchronisation per column
+        int win = 0;
+        {
+            double gv = meta[par * 8].val; int gi = meta[par * 8].idx;
+#pragma unroll
+            for (int q = 1; q < CS; ++q) {
+                const double ov = meta[par * 8 + q].val; const int oi = meta[par * 8 + q].idx;
+                if (ov > gv || (ov == gv && ov >= 0.0 && oi < gi)) { gv = ov; gi = oi; win = q; }
+            }
+        }
+        const RMeta<T> wm = meta[par * 8 + win];
+        const int pc = wm.idx, plc = pc / CS;
+        const T tauk = wm.tau;
+        const T* vcur = vcand + ((size_t)par * CS + win) * VLEN;
+        if (tid == 0) { taus[k] = tauk; dvec[k] = fabs(wm.beta); }
+        // ---- the owner warp retires the pivot column: park R'(:, k) in shared memory
+        if (rank == win && warp == (plc % CTA_WARPS)) {
+            const int us = plc / CTA_WARPS;
+            T* dst = Rst + (size_t)plc * n;
+#pragma unroll
+            for (int u = 0; u < CPW; ++u)
+                if (us == u) {
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t) {
+                        const int r = lane + 32 * t;
+                        if (r < n) dst[r] = (r < k) ? a[u][t] : mk<T>(r == k ? wm.beta : 0.0);
+                    }
+                }
+            active &= ~(1u << us);   // (its position in A*P is implied by the zero pattern of the parked column)
+        }
+        // reflector k -> global (rows > k of column k of L) through the TMA, by CTA k mod CS
+        if (rank == (k % CS) && k + 1 < n) {
+            const int r0 = (k + 1) & ~(EPV - 1);
+            if (bulk_ok) {
+                if (tid == 0) tma_store(Lg + (long long)k * ldl + r0, vcur + r0, (unsigned)((n - r0) * sizeof(T)));
+            } else {
+                for (int r = k + 1 + tid; r < n; r += CTA_THREADS) Lg[(long long)k * ldl + r] = vcur[r];
+            }
+        }
+        if (k == n - 1) break;
+        // ---- pass (registers only): w = conj(tau) v^H a ; a -= v w ; down-date the squared norms
+        if (active) {
+            const int tlo = k >> 5;   // row tiles below this hold only rows < k: v is zero there
+            T v[RPL];
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                const int r = lane + 32 * t;
+                v[t] = (t >= tlo && r < n) ? vcur[r] : mk<T>(0.0);
+            }
+            T dot[CPW];
+#pragma unroll
+            for (int u = 0; u < CPW; ++u) {
+                dot[u] = mk<T>(0.0);
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) fmacc(dot[u], conj_(v[t]), a[u][t]);
+            }
+            const T mydot = reduce_transposed<T, CPW>(dot, lane);   // lane-group u holds column u's total
+            const T myw = conj_(tauk) * mydot;
+            T w[CPW];
+#pragma unroll
+            for (int u = 0; u < CPW; ++u) w[u] = shb(myw, u * FLS);
+            // pivot-row entries a'(k, c) = a(k,c) - w (v_k(k) = 1): row k sits in lane k%32, tile k/32
+            T ak[CPW];
+#pragma unroll
+            for (int u = 0; u < CPW; ++u) ak[u] = mk<T>(0.0);
+#pragma unroll
+            for (int t = 0; t < RPL; ++t)
+                if (t == tlo) {
+#pragma unroll
+                    for (int u = 0; u < CPW; ++u) ak[u] = a[u][t];
+                }
+#pragma unroll
+            for (int u = 0; u < CPW; ++u) {
+                ak[u] = shb(ak[u], k & 31) - w[u];
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) fms(a[u][t], v[t], w[u]);
+            }
+            bool flagged = false;
+            if (leader && ((active >> myu) & 1u) && vn1 != 0.0) {
+                const T akm = pickv<T, CPW>(ak, myu);
+                const double temp = fmax(0.0, 1.0 - abs2_(akm) / vn1);
+                const double q2 = vn1 / vn2;
+                if (temp * q2 <= TOL3Z_R) flagged = true;
+                else vn1 *= temp;
+            }
+            unsigned fl = __ballot_sync(0xffffffffu, flagged);
+            while (fl) {   // exact squared norm of a flagged column below row k, straight from the registers
+                const int src = __ffs(fl) - 1;
+                fl &= fl - 1;
+                const int uf = src / FLS;
+                double ss = 0.0;
+#pragma unroll
+                for (int u = 0; u < CPW; ++u)
+                    if (uf == u) {
+#pragma unroll
+                        for (int t = 0; t < RPL; ++t) if (lane + 32 * t > k) ss += abs2_(a[u][t]);
+                    }
+                ss = warp_sum(ss);
+                if (lane == src) { vn1 = ss; vn2 = ss; }
+            }
+        }
+        select_and_publish(k + 1);
+    }
+    if (tid == 0) tma_wait_all();   // all reflectors have landed in global memory
+    __syncthreads();
+
+    // ------------------------------------------------------------------ d, R (original column order)
+    {
+        T* Rg = p.R + (long long)b * p.strideR;
+        for (int lc = warp; lc < CTA_WARPS * CPW; lc += CTA_WARPS) {
+            const int c = lc * CS + rank;
+            if (c >= n) continue;
+            const T* col = Rst + (size_t)lc * n;
+            T* dst = Rg + (long long)c * p.ldr;
+            for (int r = lane; r < n; r += 32) dst[r] = col[r] / dvec[r];   // rows below the pivot position hold 0
+        }
+        if (rank == 0) {
+            double* d = p.d + (long long)b * p.stride_d;
+            for (int r = tid; r < n; r += CTA_THREADS) d[r] = dvec[r];
+        }
+    }
+    __threadfence();
+    cl_barrier<CS>();   // every CTA's reflectors are in global memory and visible; parked columns consumed
+
+    // ------------------------------------------------------------------ Q = H_0 ... H_{n-1} applied to I
+#pragma unroll
+    for (int u = 0; u < CPW; ++u) {
+        const int c = (warp + CTA_WARPS * u) * CS + rank;
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) a[u][t] = mk<T>((lane + 32 * t == c && c < n) ? 1.0 : 0.0);
+    }
+    {
+        T* const ring = vcand;   // [2][QKC][NMAX]
+        const int nchunk = (n + QKC_R - 1) / QKC_R;
+        const bool vecq = (((size_t)ldl * sizeof(T)) % 16 == 0) && ((((uintptr_t)Lg) & 15) == 0) && (CP || (n % 2 == 0));
+        auto load_chunk = [&](int ch, int buf) {
+            T* dstb = ring + (size_t)buf * QKC_R * NMAX;
+            const int per_col = (n + EPV - 1) / EPV;
+            for (int e = tid; e < QKC_R * per_col; e += CTA_THREADS) {
+                const int i = e / per_col, r = (e % per_col) * EPV;
+                const int kk = ch * QKC_R + i;
+                T* dst = dstb + (size_t)i * NMAX + r;
+                if (kk < n && vecq) {
+                    cp_async16(dst, Lg + (long long)kk * ldl + r, 16);
+                } else if (kk < n) {
+                    for (int t = 0; t < EPV; ++t) if (r + t < n) dst[t] = Lg[(long long)kk * ldl + r + t];
+                }
+            }
+            cp_async_commit();
+        };
+        load_chunk(nchunk - 1, (nchunk - 1) & 1);
+        for (int ch = nchunk - 1; ch >= 0; --ch) {
+            if (ch > 0) load_chunk(ch - 1, (ch - 1) & 1);
+            if (ch > 0) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncthreads();
+            const T* vb = ring + (size_t)(ch & 1) * QKC_R * NMAX;
+            const int k0 = ch * QKC_R;
+            const int kcnt = min(QKC_R, n - k0);
+            // columns left of the whole chunk are untouched by it
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < CPW; ++u) {
+                const int c = (warp + CTA_WARPS * u) * CS + rank;
+                any |= (c < n) && (c >= k0);
+            }
+            if (any) {
+                const int tlo = k0 >> 5;
+                for (int i = kcnt - 1; i >= 0; --i) {
+                    const int k = k0 + i;
+                    const T* vk = vb + (size_t)i * NMAX;
+                    const T tk = taus[k];
+                    T v[RPL];
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t) {
+                        const int r = lane + 32 * t;
+                        v[t] = (t >= tlo && r < n && r > k) ? vk[r] : mk<T>(r == k ? 1.0 : 0.0);
+                    }
+                    T dot[CPW];
+#pragma unroll
+                    for (int u = 0; u < CPW; ++u) {
+                        dot[u] = mk<T>(0.0);
+#pragma unroll
+                        for (int t = 0; t < RPL; ++t) fmacc(dot[u], conj_(v[t]), a[u][t]);
+                    }
+                    const T mydot = reduce_transposed<T, CPW>(dot, lane);
+                    const T myw = tk * mydot;
+#pragma unroll
+                    for (int u = 0; u < CPW; ++u) {
+                        const T wu = shb(myw, u * FLS);
+#pragma unroll
+                        for (int t = 0; t < RPL; ++t) fms(a[u][t], v[t], wu);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    cl_barrier<CS>();   // every CTA is done reading reflectors from Lg before anyone overwrites them
+#pragma unroll
+    for (int u = 0; u < CPW; ++u) {
+        const int c = (warp + CTA_WARPS * u) * CS + rank;
+        if (c < n) {
+            T* dst = Lg + (long long)c * ldl;
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                const int r = lane + 32 * t;
+                if (r < n) dst[r] = a[u][t];
+            }
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+template <typename T, int CS, int RPL, int CPW> static cudaError_t launch_reg(const LdrArgs<T>& p, cudaStream_t stream) {
+    auto kern = ldr_reg_kernel<T, CS, RPL, CPW>;
+    const size_t smem = RegLayout<T, RPL, CPW>(p.n, CS).total;
+    if (smem > 227 * 1024) return cudaErrorNotSupported;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)p.batch * CS, 1, 1);
+    cfg.blockDim = dim3(CTA_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+    ++g_launch_count;
+    return e;
+}
+
+// register tile shapes: real 32 doubles per lane, complex 16 complex per lane
+template <typename T> struct RegShape;
+template <> struct RegShape<double> {
+    // n <= 64: RPL 2, CPW 4 (CS 1) | n <= 128: RPL 4, CPW 8 (CS 1) | n <= 256: RPL 8, CPW 4 (CS = ceil(n/64))
+    static int cluster(int n) { return n <= 128 ? 1 : (n <= 256 ? (n <= 192 ? 4 : 4) : 0); }
+};
+template <> struct RegShape<cplx> {
+    // n <= 64: RPL 2, CPW 4 (CS 1) | n <= 128: RPL 4, CPW 4 (CS 2) | n <= 256: RPL 8, CPW 2 (CS 8)
+    static int cluster(int n) { return n <= 64 ? 1 : (n <= 128 ? 2 : (n <= 256 ? 8 : 0)); }
+};
+
+template <typename T> int ldr_reg_cluster_size(int n) { return RegShape<T>::cluster(n); }
+
+template <> cudaError_t ldr_reg_batched<double>(const LdrArgs<double>& p, cudaStream_t s) {
+    if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
+    if (p.n <= 64) return launch_reg<double, 1, 2, 4>(p, s);
+    if (p.n <= 128) return launch_reg<double, 1, 4, 8>(p, s);
+    if (p.n <= 256) return launch_reg<double, 4, 8, 4>(p, s);
+    return cudaErrorNotSupported;
+}
+template <> cudaError_t ldr_reg_batched<cplx>(const LdrArgs<cplx>& p, cudaStream_t s) {
+    if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
+    if (p.n <= 64) return launch_reg<cplx, 1, 2, 4>(p, s);
+    if (p.n <= 128) return launch_reg<cplx, 2, 4, 4>(p, s);
+    if (p.n <= 256) return launch_reg<cplx, 8, 8, 2>(p, s);
+    return cudaErrorNotSupported;
+}
+
+template int ldr_reg_cluster_size<double>(int);
+template int ldr_reg_cluster_size<cplx>(int);
+
+}  // namespace sla

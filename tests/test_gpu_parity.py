@@ -422,16 +422,25 @@ def test_full_size_properties_C2(S):
     assert np.isfinite(Gh).all()
 
 
-def test_streaming_ldr_kernel_subprocess():
-    """The L2-streaming LDR kernel (used when a matrix does not fit a cluster's shared memory, e.g.
-    N=1024) is forced through SLA_LDR_STREAMING=1 in a child process and must pass the same checks."""
+@pytest.mark.parametrize("algo", ["streaming", "cluster"])
+def test_other_ldr_kernels_subprocess(algo):
+    """Default LDR kernel for n <= 256 is the register-resident cluster kernel.  The shared-memory cluster
+    kernel (256 < n <= 512, e.g. C5's N=400) and the L2-streaming kernel (larger n, e.g. C4's N=1024) are
+    forced through SLA_LDR_ALGO in a child process and must pass the same checks."""
     import os
     import subprocess
     import sys
-    if os.environ.get("SLA_LDR_STREAMING"):
+    if os.environ.get("SLA_LDR_ALGO"):
         pytest.skip("already in the child")
-    env = dict(os.environ, SLA_LDR_STREAMING="1")
+    env = dict(os.environ, SLA_LDR_ALGO=algo)
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
                         "ldr_random or ldr_graded or ldr_identity or chain_C1 or ref_lmul_matrix or small_complex"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_ldr_n512_and_n1024_paths(S):
+    """Sizes beyond the register kernel: N=400 (shared-memory cluster kernel) and N=520 (L2-streaming)."""
+    rng = np.random.default_rng(9)
+    check_ldr(S, graded_matrix(rng, 400, False, 50, 1))
+    check_ldr(S, rand_matrix(rng, 520, False, 1))
