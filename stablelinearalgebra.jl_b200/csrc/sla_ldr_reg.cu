@@ -28,12 +28,20 @@ namespace {
 constexpr double TOL3Z_R = 1.4901161193847656e-08;  // sqrt(eps), LAPACK ?laqps / ?laqp2
 constexpr int QKC_R = 8;                             // reflectors per chunk in the Q phase
 
+// Pivot candidates are compared as packed 64-bit integer keys (no FP64 compares on the critical path):
+// the bit pattern of a non-negative double is monotone, its 10 low mantissa bits are replaced by
+// (1023 - column) so that ties go to the smaller column index.  0 = "no candidate".
+__device__ __forceinline__ double nan_inf(double v) { return (v == v) ? v : INFINITY; }
+__device__ __forceinline__ unsigned long long pack_key(double v, int c) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(nan_inf(v));
+    return (b & ~0x3FFull) | (unsigned long long)(1023 - c);
+}
+__device__ __forceinline__ int key_col(unsigned long long key) { return 1023 - (int)(key & 0x3FFull); }
+
 template <typename T> struct RMeta {
-    double val;   // squared down-dated norm (-1: no active column left)
+    unsigned long long key;   // packed (squared down-dated norm, column); 0: no active column left
     double beta;
     T tau;
-    int idx;
-    int pad;
 };
 
 template <typename T, int RPL, int CPW> struct RegLayout {
@@ -69,8 +77,6 @@ __device__ __forceinline__ double shx(double v, int o) { return __shfl_xor_sync(
 __device__ __forceinline__ cplx shx(cplx v, int o) { return cplx{shx(v.re, o), shx(v.im, o)}; }
 __device__ __forceinline__ double shb(double v, int l) { return __shfl_sync(0xffffffffu, v, l); }
 __device__ __forceinline__ cplx shb(cplx v, int l) { return cplx{shb(v.re, l), shb(v.im, l)}; }
-__device__ __forceinline__ double nan_inf(double v) { return (v == v) ? v : INFINITY; }
-
 // Sum G (power of two, <= 8) per-lane values over the warp with far fewer shuffles than G butterflies:
 // each round halves the number of values a lane carries.  Afterwards every lane of lane-group u
 // (32/G consecutive lanes) holds the total of a[u].
@@ -168,8 +174,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     // squared partial norms live in the lane-group leaders' registers
     const int myu = lane / FLS;
     const bool leader = (lane % FLS) == 0;
-    double vn1 = reduce_transposed<double, CPW>(ssq, lane), vn2 = vn1;
+    double vn1 = reduce_transposed<double, CPW>(ssq, lane);
+    double ivn2 = 1.0 / vn1;   // 1 / (squared norm at the last exact computation)
     const int myc = (warp + CTA_WARPS * myu) * CS + rank;
+    unsigned long long* const ckey = reinterpret_cast<unsigned long long*>(wval);   // [16] per-warp best keys
 
     for (int r = tid; r < 2 * CS * VLEN; r += CTA_THREADS) vcand[r] = mk<T>(0.0);
     __syncthreads();
@@ -178,24 +186,30 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     // warp candidate -> shared; block barrier; the warp holding the CTA's best column builds the reflector
     // for position kpos from its registers and pushes it (plus norm, index, tau, beta) to every CTA.
     auto select_and_publish = [&](int kpos) {
-        double bv = -1.0; int bi = 0x7fffffff;
-        if (leader && ((active >> myu) & 1u)) { bv = nan_inf(vn1); bi = myc; }
-        warp_argmax(bv, bi);
-        if (lane == 0) { wval[warp] = bv; widx[warp] = bi; }
+        const int par = kpos & 1;
+        unsigned long long key = 0ull;
+        if (leader && ((active >> myu) & 1u)) key = pack_key(vn1, myc);
+#pragma unroll
+        for (int o = FLS; o < 32; o <<= 1) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+            key = ok > key ? ok : key;
+        }
+        if (lane == 0) ckey[warp] = key;
         __syncthreads();
-        double cv = wval[0]; int ci = widx[0]; int cw = 0;
+        unsigned long long ck = ckey[0];
 #pragma unroll
         for (int w = 1; w < CTA_WARPS; ++w) {
-            const double ov = wval[w]; const int oi = widx[w];
-            if (ov > cv || (ov == cv && oi < ci)) { cv = ov; ci = oi; cw = w; }
+            const unsigned long long ok = ckey[w];
+            ck = ok > ck ? ok : ck;
         }
-        const int par = kpos & 1;
-        if (ci >= n) {   // no active column left in this CTA
-            if (warp == 0 && lane < CS) cl_peer<CS>(meta, lane)[par * 8 + rank].val = -1.0;
+        if (ck == 0ull) {   // no active column left in this CTA
+            if (warp == 0 && lane < CS) cl_peer<CS>(meta, lane)[par * 8 + rank].key = 0ull;
             return;
         }
-        if (warp != cw) return;
-        const int ub = (ci / CS) / CTA_WARPS;   // which of my columns
+        const int ci = key_col(ck);
+        const int clc = ci / CS;
+        if (warp != (clc % CTA_WARPS)) return;
+        const int ub = clc / CTA_WARPS;   // which of my columns
         T x[RPL];
 #pragma unroll
         for (int t = 0; t < RPL; ++t) x[t] = a[0][t];
@@ -205,23 +219,45 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) x[t] = a[u][t];
             }
-        double ss = 0.0;
-        T alpha = mk<T>(0.0);
+        double ss = 0.0, ss2 = 0.0;
+        T xk = mk<T>(0.0);
+        const int tk = kpos >> 5;
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
             const int r = lane + 32 * t;
-            if (r > kpos) ss += abs2_(x[t]);
-            else if (r == kpos) alpha = x[t];
+            if (r > kpos) { if (t & 1) ss2 += abs2_(x[t]); else ss += abs2_(x[t]); }
+            if (t == tk) xk = x[t];
         }
-        const double xnorm2 = warp_sum(ss);
-        alpha = warp_sum(alpha);   // exactly one lane holds a non-zero alpha
+        const double xnorm2 = warp_sum(ss + ss2);
+        const T alpha = shb(xk, kpos & 31);
         T tau, scal; double beta;
         if (xnorm2 == 0.0 && imag_(alpha) == 0.0) {
             tau = mk<T>(0.0); scal = mk<T>(0.0); beta = real_(alpha);
         } else {
-            beta = -copysign(sqrt(abs2_(alpha) + xnorm2), real_(alpha));
-            tau = mk<T>((beta - real_(alpha)) / beta, -imag_(alpha) / beta);
-            scal = mk<T>(1.0) / (alpha - mk<T>(beta));
+            if constexpr (!CP) {
+                // |beta| = sqrt(s), 1/|beta| from one rsqrt + Newton steps (no sqrt/div dependency chain)
+                const double sq = fma(alpha, alpha, xnorm2);
+                double r = rsqrt(sq);
+                double bb = sq * r;
+                bb = fma(0.5 * r, fma(-bb, bb, sq), bb);          // |beta| to < 1 ulp
+                double ib = r;
+                ib = fma(ib, fma(-bb, ib, 1.0), ib);              // 1/|beta|
+                ib = fma(ib, fma(-bb, ib, 1.0), ib);
+                const double aa = fabs(alpha);
+                beta = -copysign(bb, alpha);
+                tau = fma(aa, ib, 1.0);                            // (beta - alpha)/beta = 1 + |alpha|/|beta|
+                const double den = aa + bb;                        // alpha - beta = sign(alpha) (|alpha| + |beta|)
+                scal = copysign(1.0 / den, alpha);
+                if (!(sq > 1e-280 && sq < 1e280)) {                // out of the safe range of the fast path
+                    beta = -copysign(sqrt(sq), alpha);
+                    tau = (beta - alpha) / beta;
+                    scal = 1.0 / (alpha - beta);
+                }
+            } else {
+                beta = -copysign(sqrt(abs2_(alpha) + xnorm2), real_(alpha));
+                tau = mk<T>((beta - real_(alpha)) / beta, -imag_(alpha) / beta);
+                scal = mk<T>(1.0) / (alpha - mk<T>(beta));
+            }
         }
         // rows [rz, kpos) are written as zeros (the slot still holds an older vector there and the TMA /
         // the pass read from an aligned start)
@@ -240,29 +276,39 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         }
         if (lane < CS) {
             RMeta<T> m;
-            m.val = cv; m.beta = beta; m.tau = tau; m.idx = ci; m.pad = 0;
+            m.key = ck; m.beta = beta; m.tau = tau;
             cl_peer<CS>(meta, lane)[par * 8 + rank] = m;
         }
     };
 
     select_and_publish(0);
 
+#ifdef SLA_LDR_PROFILE
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool prof = (p.prof != nullptr) && (blockIdx.x < CS);
+    long long tq = prof ? clock64() : 0;
+#define PROF_MARK(i) do { if (prof) { long long t_ = clock64(); pt[i] += t_ - tq; tq = t_; } } while (0)
+#else
+#define PROF_MARK(i) do { } while (0)
+#endif
     // ------------------------------------------------------------------ pivoted Householder QR
     for (int k = 0; k < n; ++k) {
         const int par = k & 1;
         if (tid == 0) tma_wait_read();   // the TMA is done reading the slot it was given two columns ago
+        PROF_MARK(0);
         cl_barrier<CS>();                // the ONLY cluster-wide synchronisation per column
+        PROF_MARK(1);
         int win = 0;
         {
-            double gv = meta[par * 8].val; int gi = meta[par * 8].idx;
+            unsigned long long gk = meta[par * 8].key;
 #pragma unroll
             for (int q = 1; q < CS; ++q) {
-                const double ov = meta[par * 8 + q].val; const int oi = meta[par * 8 + q].idx;
-                if (ov > gv || (ov == gv && ov >= 0.0 && oi < gi)) { gv = ov; gi = oi; win = q; }
+                const unsigned long long ok = meta[par * 8 + q].key;
+                if (ok > gk) { gk = ok; win = q; }
             }
         }
         const RMeta<T> wm = meta[par * 8 + win];
-        const int pc = wm.idx, plc = pc / CS;
+        const int pc = key_col(wm.key), plc = pc / CS;
         const T tauk = wm.tau;
         const T* vcur = vcand + ((size_t)par * CS + win) * VLEN;
         if (tid == 0) { taus[k] = tauk; dvec[k] = fabs(wm.beta); }
@@ -291,49 +337,42 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             }
         }
         if (k == n - 1) break;
+        PROF_MARK(2);
         // ---- pass (registers only): w = conj(tau) v^H a ; a -= v w ; down-date the squared norms
         if (active) {
-            const int tlo = k >> 5;   // row tiles below this hold only rows < k: v is zero there
+            const int tlo = k >> 5;   // row tiles below this hold only rows < k: v is zero there -> skipped
             T v[RPL];
-#pragma unroll
-            for (int t = 0; t < RPL; ++t) {
-                const int r = lane + 32 * t;
-                v[t] = (t >= tlo && r < n) ? vcur[r] : mk<T>(0.0);
-            }
             T dot[CPW];
-#pragma unroll
-            for (int u = 0; u < CPW; ++u) {
-                dot[u] = mk<T>(0.0);
-#pragma unroll
-                for (int t = 0; t < RPL; ++t) fmacc(dot[u], conj_(v[t]), a[u][t]);
-            }
-            const T mydot = reduce_transposed<T, CPW>(dot, lane);   // lane-group u holds column u's total
-            const T myw = conj_(tauk) * mydot;
             T w[CPW];
-#pragma unroll
-            for (int u = 0; u < CPW; ++u) w[u] = shb(myw, u * FLS);
-            // pivot-row entries a'(k, c) = a(k,c) - w (v_k(k) = 1): row k sits in lane k%32, tile k/32
             T ak[CPW];
 #pragma unroll
-            for (int u = 0; u < CPW; ++u) ak[u] = mk<T>(0.0);
-#pragma unroll
-            for (int t = 0; t < RPL; ++t)
-                if (t == tlo) {
-#pragma unroll
-                    for (int u = 0; u < CPW; ++u) ak[u] = a[u][t];
-                }
-#pragma unroll
-            for (int u = 0; u < CPW; ++u) {
-                ak[u] = shb(ak[u], k & 31) - w[u];
-#pragma unroll
-                for (int t = 0; t < RPL; ++t) fms(a[u][t], v[t], w[u]);
-            }
+            for (int u = 0; u < CPW; ++u) { dot[u] = mk<T>(0.0); ak[u] = mk<T>(0.0); }
+            // straight-line code (all loads first, full ILP) over the row tiles [T0, RPL); two variants so
+            // that the second half of the factorisation skips the tiles that hold only rows < k
+#define SLA_PASS(T0)                                                                                   \
+    {                                                                                                  \
+        _Pragma("unroll") for (int t = (T0); t < RPL; ++t)                                             \
+            v[t] = (lane + 32 * t < n) ? vcur[lane + 32 * t] : mk<T>(0.0);                             \
+        _Pragma("unroll") for (int u = 0; u < CPW; ++u)                                                \
+            _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fmacc(dot[u], conj_(v[t]), a[u][t]);    \
+        const T mydot = reduce_transposed<T, CPW>(dot, lane);                                          \
+        const T myw = conj_(tauk) * mydot;                                                             \
+        _Pragma("unroll") for (int u = 0; u < CPW; ++u) w[u] = shb(myw, u * FLS);                      \
+        _Pragma("unroll") for (int t = (T0); t < RPL; ++t)                                             \
+            if (t == tlo) { _Pragma("unroll") for (int u = 0; u < CPW; ++u) ak[u] = a[u][t]; }         \
+        _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
+            ak[u] = shb(ak[u], k & 31) - w[u];                                                         \
+            _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], w[u]);               \
+        }                                                                                              \
+    }
+            if (RPL >= 4 && tlo >= RPL / 2) SLA_PASS(RPL / 2)
+            else SLA_PASS(0)
+#undef SLA_PASS
             bool flagged = false;
             if (leader && ((active >> myu) & 1u) && vn1 != 0.0) {
                 const T akm = pickv<T, CPW>(ak, myu);
-                const double temp = fmax(0.0, 1.0 - abs2_(akm) / vn1);
-                const double q2 = vn1 / vn2;
-                if (temp * q2 <= TOL3Z_R) flagged = true;
+                const double temp = fmax(0.0, fma(-abs2_(akm), __drcp_rn(vn1), 1.0));
+                if (temp * (vn1 * ivn2) <= TOL3Z_R) flagged = true;
                 else vn1 *= temp;
             }
             unsigned fl = __ballot_sync(0xffffffffu, flagged);
@@ -349,11 +388,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                         for (int t = 0; t < RPL; ++t) if (lane + 32 * t > k) ss += abs2_(a[u][t]);
                     }
                 ss = warp_sum(ss);
-                if (lane == src) { vn1 = ss; vn2 = ss; }
+                if (lane == src) { vn1 = ss; ivn2 = 1.0 / ss; }
             }
         }
+        PROF_MARK(3);
         select_and_publish(k + 1);
     }
+    PROF_MARK(4);
     if (tid == 0) tma_wait_all();   // all reflectors have landed in global memory
     __syncthreads();
 
@@ -374,6 +415,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     }
     __threadfence();
     cl_barrier<CS>();   // every CTA's reflectors are in global memory and visible; parked columns consumed
+    PROF_MARK(5);
 
     // ------------------------------------------------------------------ Q = H_0 ... H_{n-1} applied to I
 #pragma unroll
@@ -423,32 +465,39 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                     const T* vk = vb + (size_t)i * NMAX;
                     const T tk = taus[k];
                     T v[RPL];
-#pragma unroll
-                    for (int t = 0; t < RPL; ++t) {
-                        const int r = lane + 32 * t;
-                        v[t] = (t >= tlo && r < n && r > k) ? vk[r] : mk<T>(r == k ? 1.0 : 0.0);
-                    }
                     T dot[CPW];
 #pragma unroll
-                    for (int u = 0; u < CPW; ++u) {
-                        dot[u] = mk<T>(0.0);
-#pragma unroll
-                        for (int t = 0; t < RPL; ++t) fmacc(dot[u], conj_(v[t]), a[u][t]);
-                    }
-                    const T mydot = reduce_transposed<T, CPW>(dot, lane);
-                    const T myw = tk * mydot;
-#pragma unroll
-                    for (int u = 0; u < CPW; ++u) {
-                        const T wu = shb(myw, u * FLS);
-#pragma unroll
-                        for (int t = 0; t < RPL; ++t) fms(a[u][t], v[t], wu);
-                    }
+                    for (int u = 0; u < CPW; ++u) dot[u] = mk<T>(0.0);
+#define SLA_QPASS(T0)                                                                                  \
+    {                                                                                                  \
+        _Pragma("unroll") for (int t = (T0); t < RPL; ++t) {                                           \
+            const int r_ = lane + 32 * t;                                                              \
+            v[t] = (r_ < n && r_ > k) ? vk[r_] : mk<T>(r_ == k ? 1.0 : 0.0);                           \
+        }                                                                                              \
+        _Pragma("unroll") for (int u = 0; u < CPW; ++u)                                                \
+            _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fmacc(dot[u], conj_(v[t]), a[u][t]);    \
+        const T mydot = reduce_transposed<T, CPW>(dot, lane);                                          \
+        const T myw = tk * mydot;                                                                      \
+        _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
+            const T wu = shb(myw, u * FLS);                                                            \
+            _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], wu);                 \
+        }                                                                                              \
+    }
+                    if (RPL >= 4 && tlo >= RPL / 2) SLA_QPASS(RPL / 2)
+                    else SLA_QPASS(0)
+#undef SLA_QPASS
                 }
             }
             __syncthreads();
         }
     }
+    PROF_MARK(6);
     cl_barrier<CS>();   // every CTA is done reading reflectors from Lg before anyone overwrites them
+#ifdef SLA_LDR_PROFILE
+    if (prof && (lane == 0) && (warp == 0 || warp == 1))
+        for (int i = 0; i < 8; ++i) p.prof[(rank * 2 + warp) * 8 + i] = pt[i];
+#endif
+#undef PROF_MARK
 #pragma unroll
     for (int u = 0; u < CPW; ++u) {
         const int c = (warp + CTA_WARPS * u) * CS + rank;
