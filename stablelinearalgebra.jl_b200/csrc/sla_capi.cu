@@ -130,9 +130,16 @@ template <typename T> struct Ctx {
             if (!e) return 0;
             return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : 0));
         }();
-        const bool can_reg = ldr_reg_cluster_size<T>(n) > 0, can_cl = ldr_cluster_size<T>(n) > 0;
-        if ((forced == 0 || forced == 1) && can_reg) CK(ldr_reg_batched<T>(a, s));
-        else if ((forced == 0 || forced == 1 || forced == 2) && can_cl) CK(ldr_cluster_batched<T>(a, s));
+        // Cluster kernels minimise latency (one matrix per CS SMs, ~132/CS matrices in flight), the streaming
+        // kernel maximises throughput (one matrix per SM, 148 in flight) but is ~4x (register kernel) / ~2.5x
+        // (shared-memory cluster kernel) slower per wave (profiles/ldr_kernels_r1.txt): pick by wave count.
+        const int cs_reg = ldr_reg_cluster_size<T>(n), cs_cl = ldr_cluster_size<T>(n);
+        auto waves = [](int batch_, int conc) { return (batch_ + conc - 1) / (conc > 0 ? conc : 1); };
+        const int w_stream = waves(batch, 148);
+        const bool reg_pays = cs_reg > 0 && waves(batch, 132 / cs_reg) <= 4 * w_stream;
+        const bool cl_pays = cs_cl > 0 && 2 * waves(batch, 132 / cs_cl) <= 5 * w_stream;
+        if (forced == 1 ? cs_reg > 0 : (forced == 0 && reg_pays)) CK(ldr_reg_batched<T>(a, s));
+        else if (forced == 2 ? cs_cl > 0 : (forced == 0 && cl_pays && cs_reg == 0)) CK(ldr_cluster_batched<T>(a, s));
         else CK(ldr_batched<T>(a, s));
         return 0;
     }
