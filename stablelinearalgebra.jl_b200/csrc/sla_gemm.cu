@@ -1,4 +1,6 @@
 // Instantiations + runtime dispatch of the batched DMMA GEMM (see sla_gemm.cuh).
+#include <cstdlib>
+
 #include "sla_gemm.cuh"
 #include "sla_kernels.h"
 
@@ -6,14 +8,20 @@ namespace sla {
 
 template <typename T, int OPA, int OPB> static cudaError_t gemm_pick_tile(const GemmArgs<T>& p, cudaStream_t s) {
     if constexpr (is_cplx<T>::value) {
-        if (p.M > 64 && p.N > 32) return launch_gemm_cfg<T, OPA, OPB, 128, 64, 32, 32, 8, 3>(p, s);
+        static const int force_tile_c = getenv("SLA_GEMM_TILE") ? atoi(getenv("SLA_GEMM_TILE")) : 0;   // experiments
+        if (force_tile_c == 12864) return launch_gemm_cfg<T, OPA, OPB, 128, 64, 32, 32, 8, 3>(p, s);
         return launch_gemm_cfg<T, OPA, OPB, 64, 64, 32, 32, 8, 3>(p, s);
     } else {
-        // 128x128 tiles waste (ceil(M/128)*128/M)^2; prefer 64x64 when that waste is large
-        long long t128 = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128) * 128 * 128;
-        long long t64 = (long long)((p.M + 63) / 64) * ((p.N + 63) / 64) * 64 * 64;
-        if (p.M > 64 && p.N > 64 && t128 * 10 <= t64 * 12)
-            return launch_gemm_cfg<T, OPA, OPB, 128, 128, 64, 32, 16, 3>(p, s);
+        // Measured on B200 (profiles/gemm_tiles_r1.txt): 64x64 CTA tiles with 4 warps (3-4 CTAs resident per SM)
+        // beat 128x128 with 8 warps (31.0 vs 27.7 TFLOP/s at N=256, batch 1280); 80x80 tiles avoid the padding
+        // waste when the size is a multiple of 80 but not of 64 (N=400).
+        static const int force_tile = getenv("SLA_GEMM_TILE") ? atoi(getenv("SLA_GEMM_TILE")) : 0;   // experiments
+        if (force_tile == 64) return launch_gemm_cfg<T, OPA, OPB, 64, 64, 32, 32, 16, 3>(p, s);
+        if (force_tile == 80) return launch_gemm_cfg<T, OPA, OPB, 80, 80, 40, 40, 16, 3>(p, s);
+        if (force_tile == 12864) return launch_gemm_cfg<T, OPA, OPB, 128, 64, 64, 32, 16, 3>(p, s);
+        if (force_tile == 128) return launch_gemm_cfg<T, OPA, OPB, 128, 128, 64, 32, 16, 3>(p, s);
+        auto padded = [&](int t) { return (long long)((p.M + t - 1) / t) * ((p.N + t - 1) / t) * t * t; };
+        if (padded(80) * 10 < padded(64) * 9) return launch_gemm_cfg<T, OPA, OPB, 80, 80, 40, 40, 16, 3>(p, s);
         return launch_gemm_cfg<T, OPA, OPB, 64, 64, 32, 32, 16, 3>(p, s);
     }
 }
