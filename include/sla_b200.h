@@ -109,6 +109,28 @@ SLA_API int sla_inv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, dou
 SLA_API int sla_logabsdet(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
                   double* logdet, void* sign, void* ws);
 
+/* ldiv_lu!(A, B, ws)  src/lu.jl:167-176 : A <- LU factors, B <- A^-1 B; (log|det A^-1|, sign det A^-1) */
+SLA_API int sla_ldiv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, void* B, double* logdet, void* sign,
+                        void* ws);
+/* ldiv!(U::LDR, V::Matrix, ws)  overloaded_functions.jl:388-400 : V <- U^-1 V (dense) */
+SLA_API int sla_ldiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
+                             void* V, void* ws);
+/* ldiv!(U::LDR, V::LDR, ws)     overloaded_functions.jl:437-464 : V <- U^-1 V, stabilised (U != V) */
+SLA_API int sla_ldiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, const void* UL, const double* Ud,
+                             const void* UR, void* VL, double* Vd, void* VR, void* ws);
+/* ldiv!(U::Matrix, V::LDR, ws)  overloaded_functions.jl:502-521 : V <- U^-1 V, stabilised; strideU 0 = shared U */
+SLA_API int sla_ldiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U, long long strideU, void* L,
+                             double* d, void* R, void* ws);
+/* rdiv!(U::Matrix, V::LDR, ws)  overloaded_functions.jl:549-565 : U <- U V^-1 (dense) */
+SLA_API int sla_rdiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, void* U, const void* L, const double* d,
+                             const void* R, void* ws);
+/* rdiv!(U::LDR, V::LDR, ws)     overloaded_functions.jl:603-637 : U <- U V^-1, stabilised (U != V) */
+SLA_API int sla_rdiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, double* Ud, void* UR,
+                             const void* VL, const double* Vd, const void* VR, void* ws);
+/* rdiv!(U::LDR, V::Matrix, ws)  overloaded_functions.jl:673-693 : U <- U V^-1, stabilised; strideV 0 = shared V */
+SLA_API int sla_rdiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R, const void* V,
+                             long long strideV, void* ws);
+
 /* inv_IpA!(G, A, ws)       exported_functions.jl:25-71   : G = (I + A)^-1 */
 SLA_API int sla_inv_IpA(sla_handle_t h, int dtype, int n, int batch, void* G, const void* L, const double* d,
                 const void* R, double* logdet, void* sign, void* ws);

@@ -42,6 +42,13 @@ SIGNATURES = {
     "sla_det_lu": (_i, _common + [_vp] * 4),
     "sla_inv_lu": (_i, _common + [_vp] * 4),
     "sla_logabsdet": (_i, _common + [_vp] * 6),
+    "sla_ldiv_lu": (_i, _common + [_vp] * 5),
+    "sla_ldiv_ldr_mat": (_i, _common + [_vp] * 5),
+    "sla_ldiv_ldr_ldr": (_i, _common + [_vp] * 7),
+    "sla_ldiv_mat_ldr": (_i, _common + [_vp, _ll, _vp, _vp, _vp, _vp]),
+    "sla_rdiv_mat_ldr": (_i, _common + [_vp] * 5),
+    "sla_rdiv_ldr_ldr": (_i, _common + [_vp] * 7),
+    "sla_rdiv_ldr_mat": (_i, _common + [_vp, _vp, _vp, _vp, _ll, _vp]),
     "sla_inv_IpA": (_i, _common + [_vp] * 7),
     "sla_inv_IpUV": (_i, _common + [_vp] * 10),
     "sla_inv_UpV": (_i, _common + [_vp] * 10),

@@ -23,6 +23,7 @@ from . import _lib
 __all__ = [
     "LDR", "LDRWorkspace", "to_device", "to_host", "ldr", "ldr_", "ldrs", "ldrs_", "ldr_workspace",
     "copyto_", "adjoint_", "lmul_", "rmul_", "mul_", "logabsdet", "det_lu_", "inv_lu_",
+    "ldiv_", "rdiv_", "ldiv_lu_",
     "inv_IpA_", "inv_IpUV_", "inv_UpV_", "inv_invUpV_", "gemm", "greens_chain", "check_info",
     "greens_chain_workspace_bytes", "SlaError",
 ]
@@ -290,6 +291,58 @@ def mul_(H, U, V, ws: LDRWorkspace):
     return lmul_(U, H, ws)
 
 
+def ldiv_(*args):
+    """``ldiv!`` x6 (overloaded_functions.jl:388-538): (U::LDR, V::Matrix) V := U^-1 V (388-400);
+    (U::LDR, V::LDR) stabilised (437-464); (U::Matrix, V::LDR) stabilised (502-521); the four-argument
+    forms ``ldiv_(H, U, V, ws)`` copy V into H first (408, 474, 531)."""
+    if len(args) == 4:
+        H, U, V, ws = args
+        if isinstance(H, LDR):
+            ldr_(H, V)
+        else:
+            H.copy_(V)
+        return ldiv_(U, H, ws)
+    U, V, ws = args
+    lib, h = _Handle.current()
+    if isinstance(U, LDR) and not isinstance(V, LDR):
+        _chk_ws(ws, U)
+        return _check(lib.sla_ldiv_ldr_mat(h, _dtype_code(V), U.n, U.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V),
+                                           _ptr(ws.blob)), "sla_ldiv_ldr_mat")
+    _chk_ws(ws, V)
+    code = _dtype_code(V.L)
+    if isinstance(U, LDR):
+        return _check(lib.sla_ldiv_ldr_ldr(h, code, V.n, V.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V.L), _ptr(V.d),
+                                           _ptr(V.R), _ptr(ws.blob)), "sla_ldiv_ldr_ldr")
+    return _check(lib.sla_ldiv_mat_ldr(h, code, V.n, V.batch, _ptr(U), _mat_stride(U, V), _ptr(V.L), _ptr(V.d), _ptr(V.R),
+                                       _ptr(ws.blob)), "sla_ldiv_mat_ldr")
+
+
+def rdiv_(*args):
+    """``rdiv!`` x6 (overloaded_functions.jl:549-709): (U::Matrix, V::LDR) U := U V^-1 (549-565);
+    (U::LDR, V::LDR) stabilised (603-637); (U::LDR, V::Matrix) stabilised (673-693); the four-argument
+    forms ``rdiv_(H, U, V, ws)`` copy U into H first (573, 645, 703)."""
+    if len(args) == 4:
+        H, U, V, ws = args
+        if isinstance(H, LDR):
+            ldr_(H, U)
+        else:
+            H.copy_(U)
+        return rdiv_(H, V, ws)
+    U, V, ws = args
+    lib, h = _Handle.current()
+    if not isinstance(U, LDR):
+        _chk_ws(ws, V)
+        return _check(lib.sla_rdiv_mat_ldr(h, _dtype_code(U), V.n, V.batch, _ptr(U), _ptr(V.L), _ptr(V.d), _ptr(V.R),
+                                           _ptr(ws.blob)), "sla_rdiv_mat_ldr")
+    _chk_ws(ws, U)
+    code = _dtype_code(U.L)
+    if isinstance(V, LDR):
+        return _check(lib.sla_rdiv_ldr_ldr(h, code, U.n, U.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V.L), _ptr(V.d),
+                                           _ptr(V.R), _ptr(ws.blob)), "sla_rdiv_ldr_ldr")
+    return _check(lib.sla_rdiv_ldr_mat(h, code, U.n, U.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V), _mat_stride(V, U),
+                                       _ptr(ws.blob)), "sla_rdiv_ldr_mat")
+
+
 def _scalars(F_or_A, batch, device):
     dt = F_or_A.dtype
     return (torch.empty(batch, dtype=torch.float64, device=device), torch.empty(batch, dtype=dt, device=device))
@@ -312,6 +365,16 @@ def inv_lu_(A, ws: LDRWorkspace):
     logdet, sgn = _scalars(A, A.shape[0], A.device)
     _check(lib.sla_inv_lu(h, _dtype_code(A), A.shape[1], A.shape[0], _ptr(A), _ptr(logdet), _ptr(sgn),
                           _ptr(ws.blob)), "sla_inv_lu")
+    return logdet, sgn
+
+
+def ldiv_lu_(A, B, ws: LDRWorkspace):
+    """``ldiv_lu!(A, B, ws)`` (src/lu.jl:167-176): B := A^-1 B, A := LU; returns (log|det A^-1|, sign det A^-1)."""
+    lib, h = _Handle.current()
+    _chk_ws(ws, A)
+    logdet, sgn = _scalars(A, A.shape[0], A.device)
+    _check(lib.sla_ldiv_lu(h, _dtype_code(A), A.shape[1], A.shape[0], _ptr(A), _ptr(B), _ptr(logdet), _ptr(sgn),
+                           _ptr(ws.blob)), "sla_ldiv_lu")
     return logdet, sgn
 
 

@@ -155,6 +155,24 @@ template <typename T> struct Ctx {
         CK(lu_batched<T>(a, s));
         return 0;
     }
+    // ldiv_lu!(A, B, ws) (src/lu.jl:167-176): A (destroyed) := LU, B := A^-1 B
+    int lu_solve(T* A, T* Brhs, double* logdet = nullptr, T* sign = nullptr) const {
+        LuArgs<T> a{};
+        a.A = A; a.strideA = nn; a.lda = n;
+        a.X = w.X; a.strideX = nn; a.ldx = n;
+        a.rhs = Brhs; a.strideRhs = nn; a.ldrhs = n;
+        a.logdet = logdet; a.sign = sign;
+        a.ipiv_out = nullptr; a.info = w.info;
+        a.invert = 1; a.copy_back = 0;
+        a.n = n; a.batch = batch;
+        CK(lu_batched<T>(a, s));
+        return 0;
+    }
+    // dst = src where src may be one matrix shared by the batch (stride 0)
+    int copy_strided(T* dst, const T* src, long long ssrc) const {
+        CK(scale_batched<T>(dst, nn, n, src, ssrc, n, OP_N, nullptr, 0, SCALE_NONE, nullptr, 0, SCALE_NONE, n, batch, s));
+        return 0;
+    }
     int scale(T* dst, const T* src, int op, const double* rs, int rs_mode, const double* cs, int cs_mode) const {
         CK(scale_batched<T>(dst, nn, n, src, nn, n, op, rs, n, rs_mode, cs, n, cs_mode, n, batch, s));
         return 0;
@@ -393,6 +411,90 @@ int inv_invUpV_impl(sla_handle_t h, int n, int batch, T* G, const T* UL, const d
     a.logdet = logdet; a.sign = sign; a.batch = batch;
     CK(combine_batched<T>(a, c.s));
     return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ldiv! / rdiv! family (src/overloaded_functions.jl:388-709) -- SURVEY.md section 8(f)-1
+// ---------------------------------------------------------------------------------------------
+template <typename T> int ldiv_lu_impl(sla_handle_t h, int n, int batch, T* A, T* B, double* logdet, T* sign, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    return c.lu_solve(A, B, logdet, sign);
+}
+
+// ldiv!(U::LDR, V::Matrix): V := R^-1 D^-1 L^-1 V      (:388-400)
+template <typename T>
+int ldiv_ldr_mat_impl(sla_handle_t h, int n, int batch, const T* L, const double* d, const T* R, T* V, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.copy(c.w.M, L));                                                  // :391-392
+    CKI(c.lu_solve(c.w.M, V));                                              // Lu^-1 V           (:393)
+    CKI(c.scale(V, V, OP_N, d, SCALE_DIV, nullptr, SCALE_NONE));            // Du^-1 ...         (:395)
+    CKI(c.copy(c.w.M, R));                                                  // :396-397
+    return c.lu_solve(c.w.M, V);                                            // Ru^-1 ...         (:398)
+}
+
+// ldiv!(U::LDR, V::LDR): V := U^-1 V, stabilised      (:437-464)
+template <typename T>
+int ldiv_ldr_ldr_impl(sla_handle_t h, int n, int batch, const T* UL, const double* Ud, const T* UR, T* VL,
+                      double* Vd, T* VR, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.gemm(c.w.Mpp, OP_C, UL, c.nn, OP_N, VL, c.nn, Ud, SCALE_DIV, Vd, SCALE_MUL));   // Du^-1 (Lu^H Lv) Dv  (:439-450)
+    CKI(c.copy(c.w.M, UR));                                                                // :451-452
+    CKI(c.lu_solve(c.w.M, c.w.Mpp));                                                       // Ru^-1 [...]         (:453)
+    CKI(c.ldr(VL, Vd, c.w.Mp, c.w.Mpp, c.nn));                                             // ldr!                (:456)
+    CKI(c.gemm(c.w.M, OP_N, c.w.Mp, c.nn, OP_N, VR, c.nn));                                // R0 Rv               (:459)
+    return c.copy(VR, c.w.M);                                                              //                     (:460)
+}
+
+// ldiv!(U::Matrix, V::LDR): V := U^-1 V, stabilised   (:502-521)
+template <typename T>
+int ldiv_mat_ldr_impl(sla_handle_t h, int n, int batch, const T* U, long long sU, T* VL, double* Vd, T* VR, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.scale(VL, VL, OP_N, nullptr, SCALE_NONE, Vd, SCALE_MUL));         // Lv Dv             (:508-509)
+    CKI(c.copy_strided(c.w.M, U, sU));                                      // :510
+    CKI(c.lu_solve(c.w.M, VL));                                             // U^-1 Lv Dv        (:511)
+    CKI(c.ldr(VL, Vd, c.w.Mp));                                             // ldr!              (:514)
+    CKI(c.gemm(c.w.M, OP_N, c.w.Mp, c.nn, OP_N, VR, c.nn));                 // R0 Rv             (:517)
+    return c.copy(VR, c.w.M);                                               //                   (:518)
+}
+
+// rdiv!(U::Matrix, V::LDR): U := U R^-1 D^-1 L^-1     (:549-565)
+template <typename T>
+int rdiv_mat_ldr_impl(sla_handle_t h, int n, int batch, T* U, const T* L, const double* d, const T* R, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CK(set_identity_batched<T>(c.w.Mpp, c.nn, n, n, batch, c.s));           // :551
+    CKI(c.copy(c.w.M, L));                                                  // :552-553
+    CKI(c.lu_solve(c.w.M, c.w.Mpp));                                        // Lv^-1             (:554)
+    CKI(c.scale(c.w.Mpp, c.w.Mpp, OP_N, d, SCALE_DIV, nullptr, SCALE_NONE)); // Dv^-1 Lv^-1      (:556)
+    CKI(c.copy(c.w.M, R));                                                  // :557-558
+    CKI(c.lu_solve(c.w.M, c.w.Mpp));                                        // Rv^-1 Dv^-1 Lv^-1 (:559)
+    CKI(c.gemm(c.w.Mp, OP_N, U, c.nn, OP_N, c.w.Mpp, c.nn));                // U [...]           (:560)
+    return c.copy(U, c.w.Mp);                                               //                   (:561)
+}
+
+// rdiv!(U::LDR, V::LDR): U := U V^-1, stabilised      (:603-637)
+template <typename T>
+int rdiv_ldr_ldr_impl(sla_handle_t h, int n, int batch, T* UL, double* Ud, T* UR, const T* VL, const double* Vd,
+                      const T* VR, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.copy(c.w.Mp, VR));                                                               // :606-607
+    CKI(c.lu(c.w.Mp, c.w.X, 1, 0, nullptr, nullptr));                                      // Rv^-1 -> X          (:608)
+    CKI(c.gemm(c.w.M, OP_N, UR, c.nn, OP_N, c.w.X, c.nn, Ud, SCALE_MUL, Vd, SCALE_DIV));   // Du (Ru Rv^-1) Dv^-1 (:611-620)
+    CKI(c.ldr(c.w.M, Ud, c.w.Mp));                                                         // ldr!                (:623)
+    CKI(c.gemm(c.w.Mpp, OP_N, UL, c.nn, OP_N, c.w.M, c.nn));                               // Lu L0               (:626)
+    CKI(c.copy(UL, c.w.Mpp));                                                              //                     (:627)
+    return c.gemm(UR, OP_N, c.w.Mp, c.nn, OP_C, VL, c.nn);                                 // R0 Lv^H             (:630-632)
+}
+
+// rdiv!(U::LDR, V::Matrix): U := U V^-1, stabilised   (:673-693)
+template <typename T>
+int rdiv_ldr_mat_impl(sla_handle_t h, int n, int batch, T* UL, double* Ud, T* UR, const T* V, long long sV, void* ws) {
+    Ctx<T> c(h, n, batch, ws);
+    CKI(c.copy_strided(c.w.Mp, V, sV));                                     // :680
+    CKI(c.lu(c.w.Mp, c.w.X, 1, 0, nullptr, nullptr));                       // V^-1 -> X         (:681)
+    CKI(c.gemm(c.w.M, OP_N, UR, c.nn, OP_N, c.w.X, c.nn, Ud, SCALE_MUL));   // Du (Ru V^-1)      (:682-683)
+    CKI(c.ldr(c.w.M, Ud, UR));                                              // ldr!              (:686)
+    CKI(c.gemm(c.w.Mp, OP_N, UL, c.nn, OP_N, c.w.M, c.nn));                 // Lu L0             (:689)
+    return c.copy(UL, c.w.Mp);                                              //                   (:690)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -711,6 +813,67 @@ int sla_inv_IpA(sla_handle_t h, int dtype, int n, int batch, void* G, const void
     if (!G) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -11;
     if (dtype == SLA_F64) return inv_IpA_impl<double>(h, n, batch, (double*)G, (const double*)L, d, (const double*)R, logdet, (double*)sign, ws);
     return inv_IpA_impl<cplx>(h, n, batch, (cplx*)G, (const cplx*)L, d, (const cplx*)R, logdet, (cplx*)sign, ws);
+}
+
+int sla_ldiv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, void* B, double* logdet, void* sign, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!A) return -5; if (!B) return -6; if (!ws) return -9;
+    if (dtype == SLA_F64) return ldiv_lu_impl<double>(h, n, batch, (double*)A, (double*)B, logdet, (double*)sign, ws);
+    return ldiv_lu_impl<cplx>(h, n, batch, (cplx*)A, (cplx*)B, logdet, (cplx*)sign, ws);
+}
+
+int sla_ldiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
+                     void* V, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -9;
+    if (dtype == SLA_F64) return ldiv_ldr_mat_impl<double>(h, n, batch, (const double*)L, d, (const double*)R, (double*)V, ws);
+    return ldiv_ldr_mat_impl<cplx>(h, n, batch, (const cplx*)L, d, (const cplx*)R, (cplx*)V, ws);
+}
+
+int sla_ldiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, const void* UL, const double* Ud, const void* UR,
+                     void* VL, double* Vd, void* VR, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    UV_NULLCHECK();
+    if (!ws) return -11;
+    if (UL == VL || UR == VR || Ud == Vd) return -8;
+    if (dtype == SLA_F64)
+        return ldiv_ldr_ldr_impl<double>(h, n, batch, (const double*)UL, Ud, (const double*)UR, (double*)VL, Vd, (double*)VR, ws);
+    return ldiv_ldr_ldr_impl<cplx>(h, n, batch, (const cplx*)UL, Ud, (const cplx*)UR, (cplx*)VL, Vd, (cplx*)VR, ws);
+}
+
+int sla_ldiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U, long long strideU, void* L, double* d,
+                     void* R, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!U) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10;
+    if (dtype == SLA_F64) return ldiv_mat_ldr_impl<double>(h, n, batch, (const double*)U, strideU, (double*)L, d, (double*)R, ws);
+    return ldiv_mat_ldr_impl<cplx>(h, n, batch, (const cplx*)U, strideU, (cplx*)L, d, (cplx*)R, ws);
+}
+
+int sla_rdiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, void* U, const void* L, const double* d,
+                     const void* R, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!U) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9;
+    if (dtype == SLA_F64) return rdiv_mat_ldr_impl<double>(h, n, batch, (double*)U, (const double*)L, d, (const double*)R, ws);
+    return rdiv_mat_ldr_impl<cplx>(h, n, batch, (cplx*)U, (const cplx*)L, d, (const cplx*)R, ws);
+}
+
+int sla_rdiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, double* Ud, void* UR, const void* VL,
+                     const double* Vd, const void* VR, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    UV_NULLCHECK();
+    if (!ws) return -11;
+    if (UL == VL || UR == VR || Ud == Vd) return -8;
+    if (dtype == SLA_F64)
+        return rdiv_ldr_ldr_impl<double>(h, n, batch, (double*)UL, Ud, (double*)UR, (const double*)VL, Vd, (const double*)VR, ws);
+    return rdiv_ldr_ldr_impl<cplx>(h, n, batch, (cplx*)UL, Ud, (cplx*)UR, (const cplx*)VL, Vd, (const cplx*)VR, ws);
+}
+
+int sla_rdiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R, const void* V,
+                     long long strideV, void* ws) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -10;
+    if (dtype == SLA_F64) return rdiv_ldr_mat_impl<double>(h, n, batch, (double*)L, d, (double*)R, (const double*)V, strideV, ws);
+    return rdiv_ldr_mat_impl<cplx>(h, n, batch, (cplx*)L, d, (cplx*)R, (const cplx*)V, strideV, ws);
 }
 
 #define DEFINE_UV(name, impl)                                                                                      \

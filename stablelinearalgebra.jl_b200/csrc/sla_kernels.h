@@ -30,6 +30,7 @@ template <typename T> int ldr_reg_cluster_size(int n);
 template <typename T> struct LuArgs {
     T* A; long long strideA; int lda;        // in: matrix; out: LU factors (invert=0) or A^-1 (invert=1, copy_back=1)
     T* X; long long strideX; int ldx;        // invert=1: receives A^-1 (scratch n*n per matrix)
+    T* rhs; long long strideRhs; int ldrhs;  // invert=1 and rhs != null: rhs <- A^-1 rhs (ldiv_lu!, src/lu.jl:167-176)
     double* logdet; T* sign;                 // per matrix; det A (invert=0) or det A^-1 (invert=1); may be null
     long long* ipiv_out;                     // optional 1-based pivots
     int* info;                               // optional per-matrix: 0 ok, k>0 = U(k,k) exactly zero

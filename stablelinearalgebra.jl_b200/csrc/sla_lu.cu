@@ -162,9 +162,10 @@ __device__ void lu_logdet(const T* __restrict__ A, int lda, int n, const int* ip
     __syncthreads();
 }
 
+// X = A^-1 * RHS from the LU factors (RHS = identity when rhs == nullptr, i.e. the inverse).
 template <typename T, int NB>
 __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restrict__ X, int ldx, T* Ps, T* Us,
-                           int ld, const int* ipiv, int* rowpos) {
+                           int ld, const int* ipiv, int* rowpos, const T* __restrict__ rhs, int ldrhs) {
     const int tid = threadIdx.x;
     // X = P (row-permuted identity): row r of P*I is e_{src(r)}
     for (int r = tid; r < n; r += CTA_THREADS) rowpos[r] = r;
@@ -176,7 +177,8 @@ __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restric
         }
     __syncthreads();
     for (int c = tid >> 5; c < n; c += CTA_WARPS)
-        for (int r = (tid & 31); r < n; r += 32) X[(long long)c * ldx + r] = mk<T>(rowpos[r] == c ? 1.0 : 0.0);
+        for (int r = (tid & 31); r < n; r += 32)
+            X[(long long)c * ldx + r] = rhs ? rhs[(long long)c * ldrhs + rowpos[r]] : mk<T>(rowpos[r] == c ? 1.0 : 0.0);
     __syncthreads();
     // ---- forward sweep: Y = L^-1 P
     for (int p0 = 0; p0 < n; p0 += NB) {
@@ -268,8 +270,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) lu_kernel(LuArgs<T> p) {
         for (int i = tid; i < n; i += CTA_THREADS) p.ipiv_out[(long long)b * n + i] = ipiv[i] + 1;
     if (p.invert) {
         T* X = p.X + (long long)b * p.strideX;
-        lu_inverse<T, NB>(A, p.lda, n, X, p.ldx, Ps, Us, ld, ipiv, rowpos);
-        if (p.copy_back) {
+        T* rhs = p.rhs ? p.rhs + (long long)b * p.strideRhs : nullptr;
+        lu_inverse<T, NB>(A, p.lda, n, X, p.ldx, Ps, Us, ld, ipiv, rowpos, rhs, p.ldrhs);
+        if (rhs) {   // ldiv_lu!: the solution replaces the right-hand side (src/lu.jl:167-176)
+            __syncthreads();
+            for (int c = tid >> 5; c < n; c += CTA_WARPS)
+                for (int r = (tid & 31); r < n; r += 32) rhs[(long long)c * p.ldrhs + r] = X[(long long)c * p.ldx + r];
+        } else if (p.copy_back) {
             for (int c = tid >> 5; c < n; c += CTA_WARPS)
                 for (int r = (tid & 31); r < n; r += 32) A[(long long)c * p.lda + r] = X[(long long)c * p.ldx + r];
         }

@@ -11,11 +11,11 @@ module StableLinearAlgebraB200
 
 using CUDA
 using LinearAlgebra
-import LinearAlgebra: adjoint!, lmul!, rmul!, mul!, logabsdet
+import LinearAlgebra: adjoint!, lmul!, rmul!, mul!, ldiv!, rdiv!, logabsdet
 import Base: eltype, size, copyto!
 
 export LDR, LDRWorkspace, ldr, ldr!, ldrs, ldrs!, ldr_workspace
-export inv_IpA!, inv_IpUV!, inv_UpV!, inv_invUpV!, inv_lu!, det_lu!, greens_chain!
+export inv_IpA!, inv_IpUV!, inv_UpV!, inv_invUpV!, inv_lu!, det_lu!, ldiv_lu!, greens_chain!
 
 const libsla = get(ENV, "LIBSLA_B200", "libsla_b200.so")
 const SLA_F64, SLA_C64 = Cint(0), Cint(1)
@@ -152,6 +152,49 @@ mul!(H::CuArray{T,3}, U::CuArray{T,3}, V::LDR{T}, ws::LDRWorkspace{T}) where {T}
 mul!(H::LDR{T}, U::CuArray{T}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = (copyto!(H, V); lmul!(U, H, ws))           # :338-342
 mul!(H::LDR{T}, U::LDR{T}, V::CuArray{T}, ws::LDRWorkspace{T}) where {T} = (copyto!(H, U); rmul!(H, V, ws))           # :351-355
 mul!(H::LDR{T}, U::LDR{T}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = (copyto!(H, V); lmul!(U, H, ws))               # :364-368
+
+# ---- ldiv! / rdiv! (src/overloaded_functions.jl:388-709) ---------------------------------------
+function ldiv!(U::LDR{T}, V::CuArray{T,3}, ws::LDRWorkspace{T}) where {T}     # :388-400
+    n, b = nb(U)
+    chk(ccall((:sla_ldiv_ldr_mat, libsla), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cvoid},
+              CuPtr{Cvoid}, CuPtr{Cvoid}), handle(), dtype(T), n, b, U.L, U.d, U.R, V, ws.blob), "sla_ldiv_ldr_mat")
+end
+function rdiv!(U::CuArray{T,3}, V::LDR{T}, ws::LDRWorkspace{T}) where {T}     # :549-565
+    n, b = nb(V)
+    chk(ccall((:sla_rdiv_mat_ldr, libsla), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cdouble},
+              CuPtr{Cvoid}, CuPtr{Cvoid}), handle(), dtype(T), n, b, U, V.L, V.d, V.R, ws.blob), "sla_rdiv_mat_ldr")
+end
+for (jl, sym) in ((:ldiv!, :sla_ldiv_ldr_ldr), (:rdiv!, :sla_rdiv_ldr_ldr))  # :437-464, :603-637
+    @eval function $jl(U::LDR{T}, V::LDR{T}, ws::LDRWorkspace{T}) where {T}
+        U === V && throw(ArgumentError("U and V must be distinct"))
+        n, b = nb(U)
+        chk(ccall(($(QuoteNode(sym)), libsla), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cvoid},
+                  CuPtr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cvoid}, CuPtr{Cvoid}), handle(), dtype(T), n, b, U.L, U.d, U.R, V.L, V.d, V.R, ws.blob), $(string(sym)))
+    end
+end
+function ldiv!(U::CuArray{T}, V::LDR{T}, ws::LDRWorkspace{T}) where {T}       # :502-521
+    n, b = nb(V)
+    chk(ccall((:sla_ldiv_mat_ldr, libsla), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{Cvoid}, Clonglong, CuPtr{Cvoid},
+              CuPtr{Cdouble}, CuPtr{Cvoid}, CuPtr{Cvoid}), handle(), dtype(T), n, b, U, mstride(U, n), V.L, V.d, V.R, ws.blob), "sla_ldiv_mat_ldr")
+end
+function rdiv!(U::LDR{T}, V::CuArray{T}, ws::LDRWorkspace{T}) where {T}       # :673-693
+    n, b = nb(U)
+    chk(ccall((:sla_rdiv_ldr_mat, libsla), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cvoid},
+              CuPtr{Cvoid}, Clonglong, CuPtr{Cvoid}), handle(), dtype(T), n, b, U.L, U.d, U.R, V, mstride(V, n), ws.blob), "sla_rdiv_ldr_mat")
+end
+ldiv!(H::CuArray{T,3}, U::LDR{T}, V::CuArray{T,3}, ws::LDRWorkspace{T}) where {T} = (copyto!(H, V); ldiv!(U, H, ws))   # :408-412
+ldiv!(H::LDR{T}, U::LDR{T}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = (copyto!(H, V); ldiv!(U, H, ws))               # :474-478
+ldiv!(H::LDR{T}, U::CuArray{T}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = (copyto!(H, V); ldiv!(U, H, ws))           # :531-535
+rdiv!(H::CuArray{T,3}, U::CuArray{T,3}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = (copyto!(H, U); rdiv!(H, V, ws))   # :573-577
+rdiv!(H::LDR{T}, U::LDR{T}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = (copyto!(H, U); rdiv!(H, V, ws))               # :645-649
+rdiv!(H::LDR{T}, U::LDR{T}, V::CuArray{T}, ws::LDRWorkspace{T}) where {T} = (copyto!(H, U); rdiv!(H, V, ws))           # :703-707
+function ldiv_lu!(A::CuArray{T,3}, B::CuArray{T,3}, ws::LDRWorkspace{T}) where {T}                                     # src/lu.jl:167-176
+    n, b = Cint(size(A, 1)), Cint(size(A, 3))
+    ld, sg = scalars(T, b)
+    chk(ccall((:sla_ldiv_lu, libsla), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cdouble},
+              CuPtr{Cvoid}, CuPtr{Cvoid}), handle(), dtype(T), n, b, A, B, ld, sg, ws.blob), "sla_ldiv_lu")
+    return ld, sg
+end
 
 # ---- determinants / inverses; each returns (logdet::CuVector{E}, sign::CuVector{T}) per matrix ----
 scalars(::Type{T}, b) where {T} = (CuArray{real(T)}(undef, b), CuArray{T}(undef, b))

@@ -284,6 +284,73 @@ def test_ref_rmul_ldr(S, R):                         # :184-192
     _check(S, R, G, *S.inv_IpA_(G, F, ws))
 
 
+def test_ref_ldiv_ldr(S, R):                         # :195-203
+    dB, ws, F, G = _new_F(S, R)
+    FBi = S.ldr(S.to_device(np.stack([R.Bbari] * 2)), ws)
+    for _ in range(R.Ns):
+        S.ldiv_(FBi, F, ws)
+    _check(S, R, G, *S.inv_IpA_(G, F, ws))
+
+
+def test_ref_ldiv_matrix(S, R):                      # :206-213
+    dB, ws, F, G = _new_F(S, R)
+    dBi = S.to_device(np.stack([R.Bbari] * 2))
+    for _ in range(R.Ns):
+        S.ldiv_(dBi, F, ws)
+    _check(S, R, G, *S.inv_IpA_(G, F, ws))
+    F2 = S.ldr(dB)                                   # shared (1-batch) U
+    for _ in range(R.Ns):
+        S.ldiv_(dBi[:1], F2, ws)
+    assert torch.equal(F2.d, F.d)
+
+
+def test_ref_ldiv_identity(S, R):                    # :216-219
+    dB, ws, F, G = _new_F(S, R)
+    FB = S.ldr(dB, ws)
+    A = dB.clone()
+    S.ldiv_(FB, A, ws)
+    assert approx(S.to_host(A)[0], np.eye(R.N)) and approx(S.to_host(A)[1], np.eye(R.N))
+    H = torch.empty_like(dB)                         # four-argument form
+    S.ldiv_(H, FB, dB, ws)
+    assert approx(S.to_host(H)[1], np.eye(R.N))
+
+
+def test_ref_rdiv_ldr(S, R):                         # :222-230
+    dB, ws, F, G = _new_F(S, R)
+    FBi = S.ldr(S.to_device(np.stack([R.Bbari] * 2)), ws)
+    for _ in range(R.Ns):
+        S.rdiv_(F, FBi, ws)
+    _check(S, R, G, *S.inv_IpA_(G, F, ws))
+
+
+def test_ref_rdiv_matrix(S, R):                      # :233-240
+    dB, ws, F, G = _new_F(S, R)
+    dBi = S.to_device(np.stack([R.Bbari] * 2))
+    for _ in range(R.Ns):
+        S.rdiv_(F, dBi, ws)
+    _check(S, R, G, *S.inv_IpA_(G, F, ws))
+
+
+def test_ref_rdiv_identity(S, R):                    # :243-246
+    dB, ws, F, G = _new_F(S, R)
+    FB = S.ldr(dB, ws)
+    A = dB.clone()
+    S.rdiv_(A, FB, ws)
+    assert approx(S.to_host(A)[0], np.eye(R.N)) and approx(S.to_host(A)[1], np.eye(R.N))
+
+
+def test_ldiv_lu_vs_numpy(S):
+    rng = np.random.default_rng(11)
+    for n, cx in ((5, False), (64, True), (100, False)):
+        A, B = rand_matrix(rng, n, cx, 3), rand_matrix(rng, n, cx, 3)
+        dA, dB = S.to_device(A), S.to_device(B)
+        ws = S.ldr_workspace(dA)
+        ld, sg = S.ldiv_lu_(dA, dB, ws)
+        sref, lref = np.linalg.slogdet(A)
+        assert relerr(S.to_host(dB), np.linalg.solve(A, B)) < 1e-11
+        assert np.allclose(ld.cpu().numpy(), -lref, atol=1e-9) and np.allclose(sg.cpu().numpy(), np.conj(sref), atol=1e-10)
+
+
 def test_ref_inv_IpUV(S, R):                         # :249-261
     dB, ws, F, G = _new_F(S, R)
     Fp = S.ldr(dB)
