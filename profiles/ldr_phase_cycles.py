@@ -22,6 +22,10 @@ lib.sla_debug_set_ldr_prof(None)
 p = prof.cpu().numpy().reshape(-1, 2, 8)
 names = ["tail(publish)", "cluster barrier", "pick/finalise", "pass+finish", "(end)", "extract+init", "Q phase", "writeback"]
 print(f"N={n} batch={batch} kernel {e0.elapsed_time(e1)*1e3:.0f} us")
+sp = prof.cpu().numpy()[64:72]
+if sp.sum():
+    print("select_and_publish (sum over the cluster's CTAs, lane 0; per column per CTA): " + " | ".join(
+        f"{nm} {v/n/4:.0f}" for nm, v in zip(["warp key reduce(w0)", "sync wait(w0)", "key scan(winner)", "col select+norm reduce", "scalar math", "remote stores"], sp)))
 for r in range(p.shape[0]):
     if p[r].sum() == 0: continue
     for w in range(2):

@@ -185,7 +185,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 
     // warp candidate -> shared; block barrier; the warp holding the CTA's best column builds the reflector
     // for position kpos from its registers and pushes it (plus norm, index, tau, beta) to every CTA.
+#ifdef SLA_LDR_PROFILE
+#define SP_MARK(i) do { if (p.prof && blockIdx.x < CS && lane == 0) { long long t_ = clock64(); atomicAdd((unsigned long long*)&p.prof[64 + (i)], (unsigned long long)(t_ - tsp)); tsp = t_; } } while (0)
+#else
+#define SP_MARK(i) do { } while (0)
+#endif
     auto select_and_publish = [&](int kpos) {
+#ifdef SLA_LDR_PROFILE
+        long long tsp = clock64();
+#endif
         const int par = kpos & 1;
         unsigned long long key = 0ull;
         if (leader && ((active >> myu) & 1u)) key = pack_key(vn1, myc);
@@ -195,7 +203,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             key = ok > key ? ok : key;
         }
         if (lane == 0) ckey[warp] = key;
+        if (warp == 0) SP_MARK(0);   // warp-level key reduce
         __syncthreads();
+        if (warp == 0) SP_MARK(1);   // wait for the slowest warp
         unsigned long long ck = ckey[0];
 #pragma unroll
         for (int w = 1; w < CTA_WARPS; ++w) {
@@ -210,6 +220,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         const int clc = ci / CS;
         if (warp != (clc % CTA_WARPS)) return;
         const int ub = clc / CTA_WARPS;   // which of my columns
+        SP_MARK(2);   // (winner warp) key scan
         T x[RPL];
 #pragma unroll
         for (int t = 0; t < RPL; ++t) x[t] = a[0][t];
@@ -230,6 +241,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         }
         const double xnorm2 = warp_sum(ss + ss2);
         const T alpha = shb(xk, kpos & 31);
+        SP_MARK(3);   // column select + norm reduce
         T tau, scal; double beta;
         if (xnorm2 == 0.0 && imag_(alpha) == 0.0) {
             tau = mk<T>(0.0); scal = mk<T>(0.0); beta = real_(alpha);
@@ -259,6 +271,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                 scal = mk<T>(1.0) / (alpha - mk<T>(beta));
             }
         }
+        SP_MARK(4);   // scalar math
         // rows [rz, kpos) are written as zeros (the slot still holds an older vector there and the TMA /
         // the pass read from an aligned start)
         const int rz = (kpos >= 2 ? kpos - 2 : 0) & ~(EPV - 1);
@@ -279,6 +292,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             m.key = ck; m.beta = beta; m.tau = tau;
             cl_peer<CS>(meta, lane)[par * 8 + rank] = m;
         }
+        SP_MARK(5);   // remote stores
     };
 
     select_and_publish(0);
