@@ -38,7 +38,7 @@ __device__ __forceinline__ unsigned long long pack_key(double v, int c) {
 }
 __device__ __forceinline__ int key_col(unsigned long long key) { return 1023 - (int)(key & 0x3FFull); }
 
-template <typename T> struct RMeta {
+template <typename T> struct alignas(16) RMeta {   // 32 bytes for both element types (bulk copies need 16-byte multiples)
     unsigned long long key;   // packed (squared down-dated norm, column); 0: no active column left
     double beta;
     T tau;
@@ -47,7 +47,7 @@ template <typename T> struct RMeta {
 template <typename T, int RPL, int CPW> struct RegLayout {
     static constexpr int NMAX = 32 * RPL;
     static constexpr int VLEN = NMAX + 8;
-    size_t offCand, offRst, offTau, offMeta, offD, offWval, offWidx, total;
+    size_t offCand, offRst, offTau, offMeta, offStageV, offStageM, offMbar, offD, offWval, offWidx, total;
     __host__ __device__ RegLayout(int n, int cs) {
         size_t o = 0;
         // candidate reflectors [2][cs][VLEN]; the Q-phase ring [2][QKC][NMAX] aliases this region
@@ -55,10 +55,14 @@ template <typename T, int RPL, int CPW> struct RegLayout {
         offCand = o; o += (cand > ring ? cand : ring);
         offRst = o; o += (size_t)CTA_WARPS * CPW * n * sizeof(T);   // parked R' columns [lc][n]
         offTau = o; o += (size_t)n * sizeof(T);
+        o = (o + 15) & ~(size_t)15;
         offMeta = o; o += 2 * 8 * sizeof(RMeta<T>);
+        offStageV = o; o += 2 * (size_t)VLEN * sizeof(T);     // local staging of the candidate the CTA publishes
+        offStageM = o; o += 2 * sizeof(RMeta<T>);
+        offMbar = o; o += 2 * sizeof(unsigned long long);     // one mbarrier per column parity
         o = (o + 15) & ~(size_t)15;
         offD = o; o += (size_t)n * sizeof(double);
-        offWval = o; o += 32 * sizeof(double);
+        offWval = o; o += 64 * sizeof(double);
         offWidx = o; o += 32 * sizeof(int);
         total = o + 64;
     }
@@ -118,6 +122,41 @@ __device__ __forceinline__ void tma_store(void* gdst, const void* ssrc, unsigned
 __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- mbarrier + DSMEM bulk copy (the candidate exchange of clusters with CS > 1) ----------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ unsigned map_cluster(const void* local, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+    return r;
+}
+// bulk copy local shared -> shared memory of CTA `rank`, completing `bytes` on that CTA's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(void* dst_local_addr, const void* src, unsigned bytes,
+                                                unsigned long long* bar_local_addr, unsigned rank) {
+    const unsigned dst = map_cluster(dst_local_addr, rank), bar = map_cluster(bar_local_addr, rank);
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "r"(smem_u32(src)), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 }  // namespace
 
 template <typename T, int CS, int RPL, int CPW>
@@ -133,7 +172,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     T* const vcand = reinterpret_cast<T*>(smem_raw + lay.offCand);        // [2][CS][VLEN]
     T* const Rst = reinterpret_cast<T*>(smem_raw + lay.offRst);           // [16*CPW][n]
     T* const taus = reinterpret_cast<T*>(smem_raw + lay.offTau);
-    RMeta<T>* const meta = reinterpret_cast<RMeta<T>*>(smem_raw + lay.offMeta);
+    RMeta<T>* const meta = reinterpret_cast<RMeta<T>*>(smem_raw + lay.offMeta);       // [2][8]   received
+    T* const stage_v = reinterpret_cast<T*>(smem_raw + lay.offStageV);                 // [2][VLEN] to be sent
+    RMeta<T>* const stage_m = reinterpret_cast<RMeta<T>*>(smem_raw + lay.offStageM);   // [2]
+    unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(smem_raw + lay.offMbar);
     double* const dvec = reinterpret_cast<double*>(smem_raw + lay.offD);
     double* const wval = reinterpret_cast<double*>(smem_raw + lay.offWval);
     int* const widx = reinterpret_cast<int*>(smem_raw + lay.offWidx);
@@ -177,7 +219,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     double vn1 = reduce_transposed<double, CPW>(ssq, lane);
     double ivn2 = 1.0 / vn1;   // 1 / (squared norm at the last exact computation)
     const int myc = (warp + CTA_WARPS * myu) * CS + rank;
-    unsigned long long* const ckey = reinterpret_cast<unsigned long long*>(wval);   // [16] per-warp best keys
+    unsigned long long* const ckey2 = reinterpret_cast<unsigned long long*>(wval);   // [2][16] per-warp best keys
+    const int n_al = (n + EPV - 1) & ~(EPV - 1);
+    // rows [rz, kpos) of a candidate are written as zeros: the slot still holds an older vector there and the
+    // pass / the TMA read from an aligned start
+    auto rz_of = [&](int kpos) { return (kpos >= 2 ? kpos - 2 : 0) & ~(EPV - 1); };
+    for (int r = tid; r < 2 * VLEN; r += CTA_THREADS) stage_v[r] = mk<T>(0.0);
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     for (int r = tid; r < 2 * CS * VLEN; r += CTA_THREADS) vcand[r] = mk<T>(0.0);
     __syncthreads();
@@ -202,18 +254,37 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
             key = ok > key ? ok : key;
         }
+        unsigned long long* const ckey = ckey2 + par * CTA_WARPS;
         if (lane == 0) ckey[warp] = key;
+        if (tid == 0) tma_wait_read();   // the TMA finished reading the slot that peers may overwrite from now on
         if (warp == 0) SP_MARK(0);   // warp-level key reduce
         __syncthreads();
         if (warp == 0) SP_MARK(1);   // wait for the slowest warp
-        unsigned long long ck = ckey[0];
+        unsigned long long kk[CTA_WARPS];
 #pragma unroll
-        for (int w = 1; w < CTA_WARPS; ++w) {
-            const unsigned long long ok = ckey[w];
-            ck = ok > ck ? ok : ck;
-        }
-        if (ck == 0ull) {   // no active column left in this CTA
-            if (warp == 0 && lane < CS) cl_peer<CS>(meta, lane)[par * 8 + rank].key = 0ull;
+        for (int w = 0; w < CTA_WARPS; ++w) kk[w] = ckey[w];
+#pragma unroll
+        for (int st = CTA_WARPS / 2; st > 0; st >>= 1)
+#pragma unroll
+            for (int w = 0; w < st; ++w) kk[w] = kk[w + st] > kk[w] ? kk[w + st] : kk[w];
+        const unsigned long long ck = kk[0];
+        const int rz = rz_of(kpos);
+        const unsigned vbytes = (unsigned)((n_al - rz) * sizeof(T));
+        if (ck == 0ull) {   // no active column left in this CTA: still send (same sizes) so that the byte counts match
+            if (warp == 0) {
+                if constexpr (CS > 1) {
+                    if (lane == 0) stage_m[par].key = 0ull;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane < CS) {
+                        dsmem_bulk_copy(vcand + ((size_t)par * CS + rank) * VLEN + rz, stage_v + (size_t)par * VLEN + rz, vbytes,
+                                        &mbar[par], lane);
+                        dsmem_bulk_copy(&meta[par * 8 + rank], &stage_m[par], (unsigned)sizeof(RMeta<T>), &mbar[par], lane);
+                    }
+                } else {
+                    if (lane == 0) meta[par * 8 + rank].key = 0ull;
+                }
+            }
             return;
         }
         const int ci = key_col(ck);
@@ -272,10 +343,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             }
         }
         SP_MARK(4);   // scalar math
-        // rows [rz, kpos) are written as zeros (the slot still holds an older vector there and the TMA /
-        // the pass read from an aligned start)
-        const int rz = (kpos >= 2 ? kpos - 2 : 0) & ~(EPV - 1);
-        T* slot = vcand + ((size_t)par * CS + rank) * VLEN;
+        // CS > 1: stage locally, then ONE bulk DSMEM copy per peer (async proxy) that completes on the peer's
+        // mbarrier -- no per-element remote stores, no cluster barrier
+        T* const dstv = (CS > 1) ? stage_v + (size_t)par * VLEN : vcand + ((size_t)par * CS + rank) * VLEN;
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
             const int r = lane + 32 * t;
@@ -283,14 +353,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                 T v = mk<T>(0.0);
                 if (r > kpos) v = x[t] * scal;
                 else if (r == kpos) v = mk<T>(1.0);
-#pragma unroll
-                for (int q = 0; q < CS; ++q) cl_peer<CS>(slot, q)[r] = v;
+                dstv[r] = v;
             }
         }
-        if (lane < CS) {
+        if (lane == 0) {
             RMeta<T> m;
             m.key = ck; m.beta = beta; m.tau = tau;
-            cl_peer<CS>(meta, lane)[par * 8 + rank] = m;
+            if constexpr (CS > 1) stage_m[par] = m; else meta[par * 8 + rank] = m;
+        }
+        if constexpr (CS > 1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < CS) {
+                dsmem_bulk_copy(vcand + ((size_t)par * CS + rank) * VLEN + rz, dstv + rz, vbytes, &mbar[par], lane);
+                dsmem_bulk_copy(&meta[par * 8 + rank], &stage_m[par], (unsigned)sizeof(RMeta<T>), &mbar[par], lane);
+            }
         }
         SP_MARK(5);   // remote stores
     };
@@ -308,9 +385,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     // ------------------------------------------------------------------ pivoted Householder QR
     for (int k = 0; k < n; ++k) {
         const int par = k & 1;
-        if (tid == 0) tma_wait_read();   // the TMA is done reading the slot it was given two columns ago
         PROF_MARK(0);
-        cl_barrier<CS>();                // the ONLY cluster-wide synchronisation per column
+        // the ONLY cluster-wide synchronisation per column: wait until all CS candidates have landed here
+        if constexpr (CS > 1) {
+            if (tid == 0) mbar_expect_tx(&mbar[par], (unsigned)(CS * ((n_al - rz_of(k)) * sizeof(T) + sizeof(RMeta<T>))));
+            mbar_wait(&mbar[par], (unsigned)((k >> 1) & 1));
+        } else {
+            __syncthreads();
+        }
         PROF_MARK(1);
         int win = 0;
         {
