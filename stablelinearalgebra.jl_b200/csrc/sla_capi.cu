@@ -15,6 +15,12 @@ static long long* g_ldr_prof = nullptr;   // diagnostics only (sla_debug_set_ldr
 
 struct sla_handle_s {
     cudaStream_t stream;
+    // fused driver only: a lower-priority side stream on which the group products (independent of the chain
+    // state) are built while the chain's latency-bound LDR kernels leave SMs idle; created lazily
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_start = nullptr;
+    cudaEvent_t ev_chunk[64] = {};
+    int n_events = 0;
 };
 
 namespace {
@@ -564,44 +570,69 @@ int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const
     const int half = ng / 2;
     if (inverse == SLA_INV_IPUV) CKI(set_identity_impl<T>(h, n, batch, UL, Ud, UR));
 
+    // Group products are independent of the chain state: with SLA_OVERLAP (default on) they are built in
+    // sub-chunks on a side stream and the chain waits per sub-chunk, so that GEMM CTAs fill the SMs the
+    // cluster LDR kernels cannot use.
+    static const bool overlap = [] { const char* e = getenv("SLA_OVERLAP"); return !(e && e[0] == '0'); }();
+    static const int SUB = [] { const char* e = getenv("SLA_OVERLAP_SUB"); int v = e ? atoi(e) : 2; return v > 0 ? v : 2; }();   // groups per sub-chunk
+    if (overlap && h->side == nullptr) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
+        CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+        for (int i = 0; i < 64; ++i) CK(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+        h->n_events = 64;
+    }
     for (int g0 = 0; g0 < ng; g0 += gc) {
         const int gcur = (ng - g0 < gc) ? (ng - g0) : gc;
-        const int bb = batch * gcur;  // group products built in this chunk; index = chain*gcur + gg
+        const int nsub = (gcur + SUB - 1) / SUB;
+        const bool ov = overlap && nsub <= 64;
+        cudaStream_t bs = ov ? h->side : s;
+        if (ov) {
+            CK(cudaEventRecord(h->ev_start, s));          // the buffers' previous consumers / exp(lam s) are done
+            CK(cudaStreamWaitEvent(bs, h->ev_start, 0));
+        }
         // X_1 = diag(e_1) expK ; X_i = diag(e_i) (expK X_{i-1})      (test/runtests.jl:93-100)
-        T *cur = cw.B0, *nxt = cw.B1;
-        for (int i = 0; i < n_stab; ++i) {
-            GemmArgs<T> g{};
-            const double* rs0 = cw.ev + ((long long)g0 * n_stab + i) * n;
-            if (i == 0) {
-                // one scale kernel per group of the chunk (row scaling of the shared expK)
-                for (int gg = 0; gg < gcur; ++gg) {
-                    CK(scale_batched<T>(cur + (long long)gg * nn, (long long)gcur * nn, n, expK, 0, n, OP_N,
-                                        rs0 + (long long)gg * n_stab * n, (long long)L * n, SCALE_MUL, nullptr, 0,
-                                        SCALE_NONE, n, batch, s));
+        // group-major layout: product of (group gg, chain c) lives at index gg*batch + c
+        T* fin = ((n_stab - 1) & 1) ? cw.B1 : cw.B0;
+        for (int sc = 0; sc < nsub; ++sc) {
+            const int ga = sc * SUB, gb = (ga + SUB < gcur) ? ga + SUB : gcur;
+            T *cur = cw.B0, *nxt = cw.B1;
+            for (int i = 0; i < n_stab; ++i) {
+                const double* rs0 = cw.ev + ((long long)(g0 + ga) * n_stab + i) * n;
+                if (i == 0) {
+                    for (int gg = ga; gg < gb; ++gg)
+                        CK(scale_batched<T>(cur + (long long)gg * batch * nn, nn, n, expK, 0, n, OP_N,
+                                            cw.ev + ((long long)(g0 + gg) * n_stab) * n, (long long)L * n, SCALE_MUL,
+                                            nullptr, 0, SCALE_NONE, n, batch, bs));
+                    continue;
                 }
-                continue;
+                GemmArgs<T> g{};
+                g.A = expK; g.strideA = 0; g.lda = n;
+                g.B = cur + (long long)ga * batch * nn; g.strideB = nn; g.ldb = n;
+                g.C = nxt + (long long)ga * batch * nn; g.strideC = nn; g.ldc = n;
+                g.M = g.N = g.K = n;
+                // row scaling exp(lam s) of (group gg = b / batch, chain c = b % batch), slice (g0+gg)*n_stab + i
+                g.rs = rs0; g.rs_mode = SCALE_MUL; g.rs_div = batch; g.stride_rs_hi = (long long)n_stab * n;
+                g.stride_rs = (long long)L * n;
+                g.cs = nullptr; g.cs_mode = SCALE_NONE; g.stride_cs = 0;
+                g.accumulate = 0; g.batch = batch * (gb - ga);
+                CK(gemm_batched<T>(OP_N, OP_N, g, bs));
+                T* t = cur; cur = nxt; nxt = t;
             }
-            g.A = expK; g.strideA = 0; g.lda = n;
-            g.B = cur; g.strideB = nn; g.ldb = n;
-            g.C = nxt; g.strideC = nn; g.ldc = n;
-            g.M = g.N = g.K = n;
-            g.rs = rs0; g.rs_mode = SCALE_MUL; g.rs_div = gcur; g.stride_rs_hi = (long long)L * n;
-            g.stride_rs = (long long)n_stab * n;
-            g.cs = nullptr; g.cs_mode = SCALE_NONE; g.stride_cs = 0;
-            g.accumulate = 0; g.batch = bb;
-            CK(gemm_batched<T>(OP_N, OP_N, g, s));
-            T* t = cur; cur = nxt; nxt = t;
+            if (ov) CK(cudaEventRecord(h->ev_chunk[sc], bs));
         }
         // stabilised updates  F <- B_bar_g F   (lmul!, overloaded_functions.jl:126-145) with ping-pong R
         for (int gg = 0; gg < gcur; ++gg) {
             const int g = g0 + gg;
+            if (ov && (gg % SUB) == 0) CK(cudaStreamWaitEvent(s, h->ev_chunk[gg / SUB], 0));
             const bool intoU = (inverse == SLA_INV_IPUV) && (g >= half);
             T*& XL = intoU ? UL : FL;
             T*& XR = intoU ? UR : FR;
             T*& XR2 = intoU ? UR2 : FR2;
             double* Xd = intoU ? Ud : Fd;
-            const T* Bg = cur + (long long)gg * nn;
-            CKI(c.gemm(c.w.M, OP_N, Bg, (long long)gcur * nn, OP_N, XL, nn, nullptr, SCALE_NONE, Xd, SCALE_MUL));
+            const T* Bg = fin + (long long)gg * batch * nn;
+            CKI(c.gemm(c.w.M, OP_N, Bg, nn, OP_N, XL, nn, nullptr, SCALE_NONE, Xd, SCALE_MUL));
             CKI(c.ldr(XL, Xd, c.w.Mp, c.w.M, nn));
             CKI(c.gemm(XR2, OP_N, c.w.Mp, nn, OP_N, XR, nn));
             T* t = XR; XR = XR2; XR2 = t;
@@ -654,6 +685,11 @@ int sla_create(sla_handle_t* handle, void* stream) {
 }
 
 int sla_destroy(sla_handle_t handle) {
+    if (handle) {
+        if (handle->side) cudaStreamDestroy(handle->side);
+        if (handle->ev_start) cudaEventDestroy(handle->ev_start);
+        for (int i = 0; i < handle->n_events; ++i) cudaEventDestroy(handle->ev_chunk[i]);
+    }
     delete handle;
     return 0;
 }
