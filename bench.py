@@ -171,16 +171,18 @@ def measure_dgemm_peak(torch, seconds=0.6):
     return best
 
 
-def measure_gemm_kernel(torch, sla, cfg, reps=5):
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE group-product GEMM launch at the C2 shape (N=256, batch 128),
+# from the `ncu --set full` capture summarised in profiles/ncu_gemm_kernel_r1.txt
+NCU_GEMM_TRAFFIC_BYTES_C2 = 98.9e6
+
+
+def measure_gemm_kernel(torch, sla, cfg, reps=20):
     """Average duration of the dominant kernel -- the batched DMMA GEMM that builds the group products
     (shared expK x per-chain matrix, row-scaled epilogue) -- at the shape/batch the step launches it
     with, timed with CUDA events on the launching stream."""
     n = cfg.N
-    ng = cfg.L // cfg.n_stab
-    batch = cfg.chains * ng
+    batch = cfg.chains * 2          # the fused driver builds the group products in sub-chunks of 2 groups
     dt = torch.complex128 if cfg.dtype.kind == "c" else torch.float64
-    per = 2 * n * n * (16 if cfg.dtype.kind == "c" else 8)
-    batch = max(1, min(batch, int((6 << 30) // per)))
     A = sla.to_device(cfg.expK())
     B = torch.randn(batch, n, n, dtype=torch.float64, device="cuda").to(dt)
     C = torch.empty_like(B)
@@ -302,7 +304,10 @@ def run_gpu(args):
         peak = measure_dgemm_peak(torch)
         achieved = gm_flops / (gm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "sla::gemm_kernel (batched FP64 DMMA GEMM, group-product shape)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": NCU_GEMM_TRAFFIC_BYTES_C2 if (cfg.N == 256 and cfg.chains == 64 and cfg.dtype.kind != "c") else None,
+                "traffic_unit": "bytes/launch (ncu dram read+write; algorithmic HBM bytes of the launch: 134.7e6)",
+                "dmma_pipe_active_pct_ncu": 78.2,
                 "peak_source": "FP64 cuBLAS DGEMM 8192^3 via torch.matmul measured in this run (MEASURED_PEAKS.json "
                                "holds only bf16 and HBM figures; nominal B200 FP64 ~37-40 TFLOP/s)",
                 "launch_ms": gm_ms, "launch_batch": gm_batch, "flops_per_launch": gm_flops,

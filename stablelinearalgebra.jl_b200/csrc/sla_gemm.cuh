@@ -133,6 +133,28 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(Gem
 #pragma unroll
         for (int j = 0; j < MF; ++j) { acc[i][j][0] = mk<T>(0.0); acc[i][j][1] = mk<T>(0.0); }
 
+    // scaling multipliers of this lane's rows / columns: loaded up front so that their global-memory latency
+    // hides behind the main loop instead of stalling the epilogue
+    const double* rs = nullptr;
+    if (p.rs) rs = (p.rs_div > 0) ? p.rs + (long long)(b / p.rs_div) * p.stride_rs_hi + (long long)(b % p.rs_div) * p.stride_rs
+                                  : p.rs + (long long)b * p.stride_rs;
+    const double* cs = p.cs ? p.cs + (long long)b * p.stride_cs : nullptr;
+    double rsv[MF][2], csv_[NF];
+    {
+        const int fk0 = lane & 3, fi0 = lane >> 2;
+#pragma unroll
+        for (int j = 0; j < MF; ++j) {
+            const int m = m0 + wm * WM + j * 8 + 2 * fk0;
+            rsv[j][0] = (rs && m < p.M) ? rs[m] : 1.0;
+            rsv[j][1] = (rs && m + 1 < p.M) ? rs[m + 1] : 1.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NF; ++i) {
+            const int n = n0 + wn * WN + i * 8 + fi0;
+            csv_[i] = (cs && n < p.N) ? cs[n] : 1.0;
+        }
+    }
+
     const int KT = (p.K + BK - 1) / BK;
     auto load_stage = [&](int stage, int kt) {
         T* sa = smem + stage * STAGE_ELEMS;
@@ -186,16 +208,12 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(Gem
     cp_async_wait<0>();
 
     // epilogue: lane owns C[m, m+1][n] with m = m0 + wm*WM + j*8 + 2*(lane&3), n = n0 + wn*WN + i*8 + lane/4
-    const double* rs = nullptr;
-    if (p.rs) rs = (p.rs_div > 0) ? p.rs + (long long)(b / p.rs_div) * p.stride_rs_hi + (long long)(b % p.rs_div) * p.stride_rs
-                                  : p.rs + (long long)b * p.stride_rs;
-    const double* cs = p.cs ? p.cs + (long long)b * p.stride_cs : nullptr;
     const bool vecC = ((p.ldc & 1) == 0 || sizeof(T) == 16) && ((((uintptr_t)C) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < NF; ++i) {
         const int n = n0 + wn * WN + i * 8 + fi;
         if (n >= p.N) continue;
-        const double csv = cs ? cs[n] : 1.0;
+        const double csv = csv_[i];
 #pragma unroll
         for (int j = 0; j < MF; ++j) {
             const int m = m0 + wm * WM + j * 8 + 2 * fk;
@@ -204,8 +222,8 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(Gem
             T v0 = acc[i][j][0], v1 = acc[i][j][1];
             const bool has1 = (m + 1 < p.M);
             if (rs) {
-                v0 = v0 * rs[m];
-                if (has1) v1 = v1 * rs[m + 1];
+                v0 = v0 * rsv[j][0];
+                v1 = v1 * rsv[j][1];
             }
             if (cs) {
                 v0 = v0 * csv;
