@@ -99,16 +99,28 @@ __device__ __forceinline__ void trailing_gemv(const T* __restrict__ A, int lda, 
                 double acc2[UC];
 #pragma unroll
                 for (int u = 0; u < UC; ++u) acc2[u] = 0.0;
-#pragma unroll 2
-                for (int r = (k & ~1) + 2 * sl; r < n; r += 2 * lpc) {
-                    const double2 w = *reinterpret_cast<const double2*>(v + r);
+                // chunks of 4 row steps: all UC*4 16-byte loads are issued before the first FMA (one L2 round
+                // trip per chunk instead of one per row step)
+                const bool cok[4] = {cbase < n, cbase + cpw < n, cbase + 2 * cpw < n, cbase + 3 * cpw < n};
+                for (int r0 = (k & ~1) + 2 * sl; r0 < n; r0 += 8 * lpc) {
+                    double2 a[UC][4];
 #pragma unroll
-                    for (int u = 0; u < UC; ++u) {
-                        const int c = cbase + u * cpw;
-                        if (c < n) {
-                            const double2 a = __ldcg(reinterpret_cast<const double2*>(A + (long long)c * lda + r));
-                            acc[u] = fma(a.x, w.x, acc[u]);
-                            acc2[u] = fma(a.y, w.y, acc2[u]);
+                    for (int it = 0; it < 4; ++it) {
+                        const int r = r0 + it * 2 * lpc;
+#pragma unroll
+                        for (int u = 0; u < UC; ++u)
+                            a[u][it] = (r < n && cok[u & 3])
+                                           ? __ldcg(reinterpret_cast<const double2*>(A + (long long)(cbase + u * cpw) * lda + r))
+                                           : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int r = r0 + it * 2 * lpc;
+                        const double2 w = (r < n) ? *reinterpret_cast<const double2*>(v + r) : make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int u = 0; u < UC; ++u) {
+                            acc[u] = fma(a[u][it].x, w.x, acc[u]);
+                            acc2[u] = fma(a[u][it].y, w.y, acc2[u]);
                         }
                     }
                 }
