@@ -112,6 +112,33 @@ def test_ldr_graded(S, n, decades, complex_):
     check_ldr(S, graded_matrix(rng, n, complex_, decades, 2))
 
 
+@pytest.mark.parametrize("complex_", [False, True])
+def test_tiny_sizes_and_empty_batch(S, complex_):
+    """n = 1, 2, 3 through every kernel family, and batch = 0 as a no-op (edge cases of the C ABI)."""
+    rng = np.random.default_rng(21)
+    for n in (1, 2, 3):
+        A = rand_matrix(rng, n, complex_, 2) + 2 * np.eye(n)
+        check_ldr(S, A)
+        dA = S.to_device(A)
+        ws = S.ldr_workspace(dA)
+        F = S.ldr(dA, ws)
+        G = torch.empty_like(dA)
+        ld, sg = S.inv_IpA_(G, F, ws)
+        ref = np.linalg.inv(np.eye(n)[None] + A)
+        assert relerr(S.to_host(G), ref) < 1e-12
+        s_ref, l_ref = np.linalg.slogdet(ref)
+        assert np.allclose(ld.cpu().numpy(), l_ref, atol=1e-12) and np.allclose(sg.cpu().numpy(), s_ref, atol=1e-12)
+        S.lmul_(dA, F, ws)
+        out = torch.empty_like(dA)
+        S.copyto_(out, F, ws)
+        assert relerr(S.to_host(out), A @ A) < 1e-12
+    lib = S.load()
+    from sla_b200 import api
+    _, h = api._Handle.current()
+    assert lib.sla_ldr(h, 0, 8, 0, None, None, None, None) == 0          # batch = 0: nothing to do
+    assert lib.sla_gemm(h, 0, 0, 0, 0, 4, 4, None, 1, 0, None, 1, 0, None, 1, 0, 3, 0) == -8   # still validates pointers
+
+
 def test_ldr_identity_and_zero_columns(S):
     # identity: every reflector is trivial (tau = 0); a matrix with dependent columns exercises the
     # exact-cancellation path of the norm down-date
