@@ -212,9 +212,16 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference for the CPU arm)")
+
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not os.path.exists(sla.LIB_PATH):      # fresh checkout without built artefacts: compile first (local rank 0)
+        if local == 0:
+            import __graft_entry__ as _g
+            _g.build()
+    if world > 1:
+        dist.barrier()
     cfg = get_cfg(args.config, args.chains)
     n, L, chains = cfg.N, cfg.L, cfg.chains
     dt = torch.complex128 if cfg.dtype.kind == "c" else torch.float64
