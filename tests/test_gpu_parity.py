@@ -477,6 +477,12 @@ def test_chain_C5_size_sample(S):
     check_chain(S, cfg, [0, 4095], "IpA")
 
 
+def test_chain_C4_size_short(S):
+    # N=1024 (C4's matrix size, L2-streaming LDR kernel) with a short chain so that the CPU oracle stays cheap
+    cfg = S.synthetic.HubbardConfig("C4s", 32, 40, 10, 1)
+    check_chain(S, cfg, [0], "IpA")
+
+
 def test_chain_sharding_invariance(S):
     # a chain's result must not depend on which batch/rank it is evaluated in
     cfg = S.synthetic.HubbardConfig("s", 8, 40, 10, 6)
