@@ -324,13 +324,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                 double bb = sq * r;
                 bb = fma(0.5 * r, fma(-bb, bb, sq), bb);          // |beta| to < 1 ulp
                 double ib = r;
-                ib = fma(ib, fma(-bb, ib, 1.0), ib);              // 1/|beta|
-                ib = fma(ib, fma(-bb, ib, 1.0), ib);
+                ib = fma(ib, fma(-bb, ib, 1.0), ib);              // 1/|beta| (r is already ~1 ulp; one correction)
                 const double aa = fabs(alpha);
                 beta = -copysign(bb, alpha);
                 tau = fma(aa, ib, 1.0);                            // (beta - alpha)/beta = 1 + |alpha|/|beta|
                 const double den = aa + bb;                        // alpha - beta = sign(alpha) (|alpha| + |beta|)
-                scal = copysign(1.0 / den, alpha);
+                double id = __drcp_rn(den);                        // correctly rounded reciprocal, no division slow path
+                scal = copysign(id, alpha);
                 if (!(sq > 1e-280 && sq < 1e280)) {                // out of the safe range of the fast path
                     beta = -copysign(sqrt(sq), alpha);
                     tau = (beta - alpha) / beta;
@@ -395,15 +395,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         }
         PROF_MARK(1);
         int win = 0;
-        {
-            unsigned long long gk = meta[par * 8].key;
+        RMeta<T> wm = meta[par * 8];
 #pragma unroll
-            for (int q = 1; q < CS; ++q) {
-                const unsigned long long ok = meta[par * 8 + q].key;
-                if (ok > gk) { gk = ok; win = q; }
-            }
+        for (int q = 1; q < CS; ++q) {
+            const RMeta<T> om = meta[par * 8 + q];   // independent loads: issued together
+            if (om.key > wm.key) { wm = om; win = q; }
         }
-        const RMeta<T> wm = meta[par * 8 + win];
         const int pc = key_col(wm.key), plc = pc / CS;
         const T tauk = wm.tau;
         const T* vcur = vcand + ((size_t)par * CS + win) * VLEN;
@@ -449,8 +446,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     {                                                                                                  \
         _Pragma("unroll") for (int t = (T0); t < RPL; ++t)                                             \
             v[t] = (lane + 32 * t < n) ? vcur[lane + 32 * t] : mk<T>(0.0);                             \
-        _Pragma("unroll") for (int u = 0; u < CPW; ++u)                                                \
-            _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fmacc(dot[u], conj_(v[t]), a[u][t]);    \
+        _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
+            T d2_ = mk<T>(0.0);                                                                        \
+            _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                                    \
+                fmacc(dot[u], conj_(v[t]), a[u][t]);                                                   \
+                if (t + 1 < RPL) fmacc(d2_, conj_(v[t + 1]), a[u][t + 1]);                             \
+            }                                                                                          \
+            dot[u] = dot[u] + d2_;                                                                     \
+        }                                                                                              \
         const T mydot = reduce_transposed<T, CPW>(dot, lane);                                          \
         const T myw = conj_(tauk) * mydot;                                                             \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) w[u] = shb(myw, u * FLS);                      \
