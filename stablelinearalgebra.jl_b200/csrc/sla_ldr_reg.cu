@@ -47,23 +47,22 @@ template <typename T> struct alignas(16) RMeta {   // 32 bytes for both element 
 template <typename T, int RPL, int CPW> struct RegLayout {
     static constexpr int NMAX = 32 * RPL;
     static constexpr int VLEN = NMAX + 8;
-    size_t offCand, offRst, offTau, offMeta, offStageV, offStageM, offMbar, offD, offWval, offWidx, total;
+    size_t offCand, offRst, offTau, offStageV, offMbar, offD, offKeys, total;
     __host__ __device__ RegLayout(int n, int cs) {
         size_t o = 0;
-        // candidate reflectors [2][cs][VLEN]; the Q-phase ring [2][QKC][NMAX] aliases this region
+        // candidate reflectors [2][cs][VLEN] (a slot = the vector, then its RMeta at element n_al); the
+        // Q-phase ring [2][QKC][NMAX] aliases this region
         size_t cand = 2 * (size_t)cs * VLEN * sizeof(T), ring = 2 * (size_t)QKC_R * NMAX * sizeof(T);
         offCand = o; o += (cand > ring ? cand : ring);
         offRst = o; o += (size_t)CTA_WARPS * CPW * n * sizeof(T);   // parked R' columns [lc][n]
         offTau = o; o += (size_t)n * sizeof(T);
         o = (o + 15) & ~(size_t)15;
-        offMeta = o; o += 2 * 8 * sizeof(RMeta<T>);
         offStageV = o; o += 2 * (size_t)VLEN * sizeof(T);     // local staging of the candidate the CTA publishes
-        offStageM = o; o += 2 * sizeof(RMeta<T>);
         offMbar = o; o += 2 * sizeof(unsigned long long);     // one mbarrier per column parity
         o = (o + 15) & ~(size_t)15;
         offD = o; o += (size_t)n * sizeof(double);
-        offWval = o; o += 64 * sizeof(double);
-        offWidx = o; o += 32 * sizeof(int);
+        o = (o + 15) & ~(size_t)15;
+        offKeys = o; o += 2 * (size_t)CTA_WARPS * CPW * sizeof(unsigned long long);   // [2][16*CPW] pivot keys
         total = o + 64;
     }
 };
@@ -172,13 +171,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     T* const vcand = reinterpret_cast<T*>(smem_raw + lay.offCand);        // [2][CS][VLEN]
     T* const Rst = reinterpret_cast<T*>(smem_raw + lay.offRst);           // [16*CPW][n]
     T* const taus = reinterpret_cast<T*>(smem_raw + lay.offTau);
-    RMeta<T>* const meta = reinterpret_cast<RMeta<T>*>(smem_raw + lay.offMeta);       // [2][8]   received
     T* const stage_v = reinterpret_cast<T*>(smem_raw + lay.offStageV);                 // [2][VLEN] to be sent
-    RMeta<T>* const stage_m = reinterpret_cast<RMeta<T>*>(smem_raw + lay.offStageM);   // [2]
     unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(smem_raw + lay.offMbar);
     double* const dvec = reinterpret_cast<double*>(smem_raw + lay.offD);
-    double* const wval = reinterpret_cast<double*>(smem_raw + lay.offWval);
-    int* const widx = reinterpret_cast<int*>(smem_raw + lay.offWidx);
+    unsigned long long* const ckey2 = reinterpret_cast<unsigned long long*>(smem_raw + lay.offKeys);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int rank = 0;
@@ -219,8 +215,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     double vn1 = reduce_transposed<double, CPW>(ssq, lane);
     double ivn2 = 1.0 / vn1;   // 1 / (squared norm at the last exact computation)
     const int myc = (warp + CTA_WARPS * myu) * CS + rank;
-    unsigned long long* const ckey2 = reinterpret_cast<unsigned long long*>(wval);   // [2][16] per-warp best keys
     const int n_al = (n + EPV - 1) & ~(EPV - 1);
+    constexpr int NKEY = CTA_WARPS * CPW;   // one key slot per (warp, column)
+    constexpr int KPL = NKEY / 32;          // keys a lane scans
+    static_assert(CPW == 2 || CPW == 4 || CPW == 8, "CPW");
+    // the RMeta of a candidate travels right behind its vector (one bulk copy per peer)
+    auto slot_meta = [&](T* slot) { return reinterpret_cast<RMeta<T>*>(slot + n_al); };
     // rows [rz, kpos) of a candidate are written as zeros: the slot still holds an older vector there and the
     // pass / the TMA read from an aligned start
     auto rz_of = [&](int kpos) { return (kpos >= 2 ? kpos - 2 : 0) & ~(EPV - 1); };
@@ -237,6 +237,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 
     // warp candidate -> shared; block barrier; the warp holding the CTA's best column builds the reflector
     // for position kpos from its registers and pushes it (plus norm, index, tau, beta) to every CTA.
+#ifdef SLA_LDR_TRACE
+#define TR(kk, ev) do { if (p.prof && blockIdx.x == 0 && lane == 0 && (kk) >= 100 && (kk) < 104) p.prof[128 + (((kk) - 100) * 16 + warp) * 12 + (ev)] = clock64(); } while (0)
+#else
+#define TR(kk, ev) do { } while (0)
+#endif
 #ifdef SLA_LDR_PROFILE
 #define SP_MARK(i) do { if (p.prof && blockIdx.x < CS && lane == 0) { long long t_ = clock64(); atomicAdd((unsigned long long*)&p.prof[64 + (i)], (unsigned long long)(t_ - tsp)); tsp = t_; } } while (0)
 #else
@@ -247,42 +252,47 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         long long tsp = clock64();
 #endif
         const int par = kpos & 1;
-        unsigned long long key = 0ull;
-        if (leader && ((active >> myu) & 1u)) key = pack_key(vn1, myc);
-#pragma unroll
-        for (int o = FLS; o < 32; o <<= 1) {
-            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
-            key = ok > key ? ok : key;
-        }
-        unsigned long long* const ckey = ckey2 + par * CTA_WARPS;
-        if (lane == 0) ckey[warp] = key;
+        unsigned long long* const ckey = ckey2 + par * NKEY;
+        if (leader) ckey[warp * CPW + myu] = ((active >> myu) & 1u) ? pack_key(vn1, myc) : 0ull;
+        TR(kpos - 1, 5);
         if (tid == 0) tma_wait_read();   // the TMA finished reading the slot that peers may overwrite from now on
-        if (warp == 0) SP_MARK(0);   // warp-level key reduce
+        if (warp == 0) SP_MARK(0);   // key store
         __syncthreads();
         if (warp == 0) SP_MARK(1);   // wait for the slowest warp
-        unsigned long long kk[CTA_WARPS];
-#pragma unroll
-        for (int w = 0; w < CTA_WARPS; ++w) kk[w] = ckey[w];
-#pragma unroll
-        for (int st = CTA_WARPS / 2; st > 0; st >>= 1)
-#pragma unroll
-            for (int w = 0; w < st; ++w) kk[w] = kk[w + st] > kk[w] ? kk[w + st] : kk[w];
-        const unsigned long long ck = kk[0];
+        TR(kpos - 1, 6);
+        // CTA-wide argmax of the NKEY keys: KPL keys per lane, then two 32-bit warp reductions (high word first)
+        unsigned long long km;
+        if constexpr (KPL == 1) {
+            km = ckey[lane];
+        } else {
+            const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(ckey + lane * KPL);
+            km = q0.x > q0.y ? q0.x : q0.y;
+            if constexpr (KPL == 4) {
+                const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(ckey + lane * KPL + 2);
+                const unsigned long long k1 = q1.x > q1.y ? q1.x : q1.y;
+                km = k1 > km ? k1 : km;
+            }
+        }
+        const unsigned khi = (unsigned)(km >> 32);
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, khi == mhi ? (unsigned)km : 0u);
+        const unsigned long long ck = ((unsigned long long)mhi << 32) | mlo;
+        TR(kpos - 1, 7);
         const int rz = rz_of(kpos);
-        const unsigned vbytes = (unsigned)((n_al - rz) * sizeof(T));
+        const unsigned cbytes = (unsigned)((n_al - rz) * sizeof(T) + sizeof(RMeta<T>));   // vector tail + meta
         if (ck == 0ull) {   // no active column left in this CTA: still send (same sizes) so that the byte counts match
             if (warp == 0) {
                 if constexpr (CS > 1) {
-                    if (lane == 0) stage_m[par].key = 0ull;
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane < CS) {
-                        dsmem_bulk_copy(vcand + ((size_t)par * CS + rank) * VLEN + rz, stage_v + (size_t)par * VLEN + rz, vbytes,
-                                        &mbar[par], lane);
-                        dsmem_bulk_copy(&meta[par * 8 + rank], &stage_m[par], (unsigned)sizeof(RMeta<T>), &mbar[par], lane);
+                    T* const st = stage_v + (size_t)par * VLEN;
+                    if (lane == 0) {
+                        slot_meta(st)->key = 0ull;
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+                        for (int q = 0; q < CS; ++q)
+                            dsmem_bulk_copy(vcand + ((size_t)par * CS + rank) * VLEN + rz, st + rz, cbytes, &mbar[par], q);
                     }
                 } else {
-                    if (lane == 0) meta[par * 8 + rank].key = 0ull;
+                    if (lane == 0) slot_meta(vcand + (size_t)par * VLEN)->key = 0ull;
                 }
             }
             return;
@@ -301,17 +311,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) x[t] = a[u][t];
             }
-        double ss = 0.0, ss2 = 0.0;
+        double sq_[RPL];
         T xk = mk<T>(0.0);
         const int tk = kpos >> 5;
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
             const int r = lane + 32 * t;
-            if (r > kpos) { if (t & 1) ss2 += abs2_(x[t]); else ss += abs2_(x[t]); }
+            sq_[t] = (r > kpos) ? abs2_(x[t]) : 0.0;
             if (t == tk) xk = x[t];
         }
-        const double xnorm2 = warp_sum(ss + ss2);
+#pragma unroll
+        for (int st = RPL / 2; st > 0; st >>= 1)
+#pragma unroll
+            for (int t = 0; t < st; ++t) sq_[t] += sq_[t + st];
+        const double xnorm2 = warp_sum(sq_[0]);
         const T alpha = shb(xk, kpos & 31);
+        TR(kpos - 1, 8);
         SP_MARK(3);   // column select + norm reduce
         T tau, scal; double beta;
         if (xnorm2 == 0.0 && imag_(alpha) == 0.0) {
@@ -343,6 +358,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             }
         }
         SP_MARK(4);   // scalar math
+        TR(kpos - 1, 9);
         // CS > 1: stage locally, then ONE bulk DSMEM copy per peer (async proxy) that completes on the peer's
         // mbarrier -- no per-element remote stores, no cluster barrier
         T* const dstv = (CS > 1) ? stage_v + (size_t)par * VLEN : vcand + ((size_t)par * CS + rank) * VLEN;
@@ -359,16 +375,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         if (lane == 0) {
             RMeta<T> m;
             m.key = ck; m.beta = beta; m.tau = tau;
-            if constexpr (CS > 1) stage_m[par] = m; else meta[par * 8 + rank] = m;
+            *slot_meta(dstv) = m;
         }
         if constexpr (CS > 1) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane < CS) {
-                dsmem_bulk_copy(vcand + ((size_t)par * CS + rank) * VLEN + rz, dstv + rz, vbytes, &mbar[par], lane);
-                dsmem_bulk_copy(&meta[par * 8 + rank], &stage_m[par], (unsigned)sizeof(RMeta<T>), &mbar[par], lane);
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < CS; ++q)
+                    dsmem_bulk_copy(vcand + ((size_t)par * CS + rank) * VLEN + rz, dstv + rz, cbytes, &mbar[par], q);
             }
         }
+        TR(kpos - 1, 10);
         SP_MARK(5);   // remote stores
     };
 
@@ -394,11 +412,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             __syncthreads();
         }
         PROF_MARK(1);
+        TR(k, 0);
         int win = 0;
-        RMeta<T> wm = meta[par * 8];
+        RMeta<T> wm = *slot_meta(vcand + (size_t)par * CS * VLEN);
 #pragma unroll
         for (int q = 1; q < CS; ++q) {
-            const RMeta<T> om = meta[par * 8 + q];   // independent loads: issued together
+            const RMeta<T> om = *slot_meta(vcand + ((size_t)par * CS + q) * VLEN);   // independent loads: issued together
             if (om.key > wm.key) { wm = om; win = q; }
         }
         const int pc = key_col(wm.key), plc = pc / CS;
@@ -430,6 +449,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             }
         }
         if (k == n - 1) break;
+        TR(k, 1);
         PROF_MARK(2);
         // ---- pass (registers only): w = conj(tau) v^H a ; a -= v w ; down-date the squared norms
         if (active) {
@@ -440,33 +460,43 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             T ak[CPW];
 #pragma unroll
             for (int u = 0; u < CPW; ++u) { dot[u] = mk<T>(0.0); ak[u] = mk<T>(0.0); }
-            // straight-line code (all loads first, full ILP) over the row tiles [T0, RPL); two variants so
-            // that the second half of the factorisation skips the tiles that hold only rows < k
+            // straight-line code (all loads first, full ILP) over the row tiles [T0, RPL), one variant per
+            // pair of tiles so that tiles holding only rows < k are skipped; retired columns are skipped too
+            // (warp-uniform branches), so the FP64 work shrinks with the active (n-k) x (n-k) block
 #define SLA_PASS(T0)                                                                                   \
     {                                                                                                  \
         _Pragma("unroll") for (int t = (T0); t < RPL; ++t)                                             \
             v[t] = (lane + 32 * t < n) ? vcur[lane + 32 * t] : mk<T>(0.0);                             \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
-            T d2_ = mk<T>(0.0);                                                                        \
-            _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                                    \
-                fmacc(dot[u], conj_(v[t]), a[u][t]);                                                   \
-                if (t + 1 < RPL) fmacc(d2_, conj_(v[t + 1]), a[u][t + 1]);                             \
+            if ((active >> u) & 1u) {                                                                  \
+                T d2_ = mk<T>(0.0);                                                                    \
+                _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                                \
+                    fmacc(dot[u], conj_(v[t]), a[u][t]);                                               \
+                    if (t + 1 < RPL) fmacc(d2_, conj_(v[t + 1]), a[u][t + 1]);                         \
+                }                                                                                      \
+                dot[u] = dot[u] + d2_;                                                                 \
             }                                                                                          \
-            dot[u] = dot[u] + d2_;                                                                     \
         }                                                                                              \
+        TR(k, 2);                                                                                      \
         const T mydot = reduce_transposed<T, CPW>(dot, lane);                                          \
         const T myw = conj_(tauk) * mydot;                                                             \
+        TR(k, 3);                                                                                      \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) w[u] = shb(myw, u * FLS);                      \
-        _Pragma("unroll") for (int t = (T0); t < RPL; ++t)                                             \
+        _Pragma("unroll") for (int t = (T0); t < RPL && t < (T0) + 2; ++t)                             \
             if (t == tlo) { _Pragma("unroll") for (int u = 0; u < CPW; ++u) ak[u] = a[u][t]; }         \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
             ak[u] = shb(ak[u], k & 31) - w[u];                                                         \
-            _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], w[u]);               \
+            if ((active >> u) & 1u) {                                                                  \
+                _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], w[u]);           \
+            }                                                                                          \
         }                                                                                              \
     }
-            if (RPL >= 4 && tlo >= RPL / 2) SLA_PASS(RPL / 2)
+            if (RPL > 6 && tlo >= 6) SLA_PASS(6)
+            else if (RPL > 4 && tlo >= 4) SLA_PASS(4)
+            else if (RPL > 2 && tlo >= 2) SLA_PASS(2)
             else SLA_PASS(0)
 #undef SLA_PASS
+            TR(k, 4);
             bool flagged = false;
             if (leader && ((active >> myu) & 1u) && vn1 != 0.0) {
                 const T akm = pickv<T, CPW>(ak, myu);
@@ -551,13 +581,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             const int k0 = ch * QKC_R;
             const int kcnt = min(QKC_R, n - k0);
             // columns left of the whole chunk are untouched by it
-            bool any = false;
+            unsigned qact = 0;
 #pragma unroll
             for (int u = 0; u < CPW; ++u) {
                 const int c = (warp + CTA_WARPS * u) * CS + rank;
-                any |= (c < n) && (c >= k0);
+                if ((c < n) && (c >= k0)) qact |= 1u << u;
             }
-            if (any) {
+            if (qact) {
                 const int tlo = k0 >> 5;
                 for (int i = kcnt - 1; i >= 0; --i) {
                     const int k = k0 + i;
@@ -573,16 +603,28 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             const int r_ = lane + 32 * t;                                                              \
             v[t] = (r_ < n && r_ > k) ? vk[r_] : mk<T>(r_ == k ? 1.0 : 0.0);                           \
         }                                                                                              \
-        _Pragma("unroll") for (int u = 0; u < CPW; ++u)                                                \
-            _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fmacc(dot[u], conj_(v[t]), a[u][t]);    \
+        _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
+            if ((qact >> u) & 1u) {                                                                    \
+                T d2_ = mk<T>(0.0);                                                                    \
+                _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                                \
+                    fmacc(dot[u], conj_(v[t]), a[u][t]);                                               \
+                    if (t + 1 < RPL) fmacc(d2_, conj_(v[t + 1]), a[u][t + 1]);                         \
+                }                                                                                      \
+                dot[u] = dot[u] + d2_;                                                                 \
+            }                                                                                          \
+        }                                                                                              \
         const T mydot = reduce_transposed<T, CPW>(dot, lane);                                          \
         const T myw = tk * mydot;                                                                      \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
             const T wu = shb(myw, u * FLS);                                                            \
-            _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], wu);                 \
+            if ((qact >> u) & 1u) {                                                                    \
+                _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], wu);             \
+            }                                                                                          \
         }                                                                                              \
     }
-                    if (RPL >= 4 && tlo >= RPL / 2) SLA_QPASS(RPL / 2)
+                    if (RPL > 6 && tlo >= 6) SLA_QPASS(6)
+                    else if (RPL > 4 && tlo >= 4) SLA_QPASS(4)
+                    else if (RPL > 2 && tlo >= 2) SLA_QPASS(2)
                     else SLA_QPASS(0)
 #undef SLA_QPASS
                 }
