@@ -27,6 +27,8 @@ namespace {
 
 constexpr double TOL3Z_R = 1.4901161193847656e-08;  // sqrt(eps), LAPACK ?laqps / ?laqp2
 constexpr int QKC_R = 8;                             // reflectors per chunk in the Q phase
+// an empty volatile asm cannot be speculated: keeps a warp-uniform `if` a real branch (no if-conversion into selects)
+#define SLA_KEEP_BRANCH asm volatile("")
 
 // Pivot candidates are compared as packed 64-bit integer keys (no FP64 compares on the critical path):
 // the bit pattern of a non-negative double is monotone, its 10 low mantissa bits are replaced by
@@ -44,27 +46,25 @@ template <typename T> struct alignas(16) RMeta {   // 32 bytes for both element 
     T tau;
 };
 
-template <typename T, int RPL, int CPW> struct RegLayout {
+// Shared-memory layout, fixed at compile time (sized for NMAX, not n) so that every address in the per-column
+// chain is base + immediate.
+template <typename T, int RPL, int CPW, int CS> struct RegLayout {
     static constexpr int NMAX = 32 * RPL;
     static constexpr int VLEN = NMAX + 8;
-    size_t offCand, offRst, offTau, offStageV, offMbar, offD, offKeys, total;
-    __host__ __device__ RegLayout(int n, int cs) {
-        size_t o = 0;
-        // candidate reflectors [2][cs][VLEN] (a slot = the vector, then its RMeta at element n_al); the
-        // Q-phase ring [2][QKC][NMAX] aliases this region
-        size_t cand = 2 * (size_t)cs * VLEN * sizeof(T), ring = 2 * (size_t)QKC_R * NMAX * sizeof(T);
-        offCand = o; o += (cand > ring ? cand : ring);
-        offRst = o; o += (size_t)CTA_WARPS * CPW * n * sizeof(T);   // parked R' columns [lc][n]
-        offTau = o; o += (size_t)n * sizeof(T);
-        o = (o + 15) & ~(size_t)15;
-        offStageV = o; o += 2 * (size_t)VLEN * sizeof(T);     // local staging of the candidate the CTA publishes
-        offMbar = o; o += 2 * sizeof(unsigned long long);     // one mbarrier per column parity
-        o = (o + 15) & ~(size_t)15;
-        offD = o; o += (size_t)n * sizeof(double);
-        o = (o + 15) & ~(size_t)15;
-        offKeys = o; o += 2 * (size_t)CTA_WARPS * CPW * sizeof(unsigned long long);   // [2][16*CPW] pivot keys
-        total = o + 64;
-    }
+    static constexpr size_t al16(size_t o) { return (o + 15) & ~(size_t)15; }
+    // candidate reflectors [2][CS][VLEN] (a slot = the vector, then its RMeta at element n_al); the
+    // Q-phase ring [2][QKC][NMAX] aliases this region
+    static constexpr size_t candBytes = 2 * (size_t)CS * VLEN * sizeof(T), ringBytes = 2 * (size_t)QKC_R * NMAX * sizeof(T);
+    static constexpr size_t offCand = 0;
+    static constexpr size_t offRst = offCand + (candBytes > ringBytes ? candBytes : ringBytes);   // parked (raw) pivot columns [lc][NMAX]
+    static constexpr size_t offTau = offRst + (size_t)CTA_WARPS * CPW * NMAX * sizeof(T);
+    static constexpr size_t offStageV = al16(offTau + (size_t)NMAX * sizeof(T));   // [2][VLEN] staging of the published candidate
+    static constexpr size_t offMbar = offStageV + 2 * (size_t)VLEN * sizeof(T);    // one mbarrier per column parity
+    static constexpr size_t offD = al16(offMbar + 2 * sizeof(unsigned long long));
+    static constexpr size_t offBeta = offD + (size_t)NMAX * sizeof(double);        // signed beta_k = R'(k, pivot column k)
+    static constexpr size_t offKeys = al16(offBeta + (size_t)NMAX * sizeof(double));   // [2][16*CPW] pivot keys
+    static constexpr size_t offPos = offKeys + 2 * (size_t)CTA_WARPS * CPW * sizeof(unsigned long long);   // pivot position per local column
+    static constexpr size_t total = offPos + (size_t)CTA_WARPS * CPW * sizeof(int) + 64;
 };
 
 template <int CS> __device__ __forceinline__ void cl_barrier() {
@@ -160,21 +160,22 @@ __device__ __forceinline__ void dsmem_bulk_copy(void* dst_local_addr, const void
 
 template <typename T, int CS, int RPL, int CPW>
 __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
-    using Lay = RegLayout<T, RPL, CPW>;
+    using Lay = RegLayout<T, RPL, CPW, CS>;
     constexpr int NMAX = Lay::NMAX, VLEN = Lay::VLEN;
     constexpr int FLS = 32 / CPW;                 // lanes per lane-group; lane u*FLS leads column u of the warp
     constexpr bool CP = is_cplx<T>::value;
     constexpr int EPV = CP ? 1 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n;
-    const Lay lay(n, CS);
-    T* const vcand = reinterpret_cast<T*>(smem_raw + lay.offCand);        // [2][CS][VLEN]
-    T* const Rst = reinterpret_cast<T*>(smem_raw + lay.offRst);           // [16*CPW][n]
-    T* const taus = reinterpret_cast<T*>(smem_raw + lay.offTau);
-    T* const stage_v = reinterpret_cast<T*>(smem_raw + lay.offStageV);                 // [2][VLEN] to be sent
-    unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(smem_raw + lay.offMbar);
-    double* const dvec = reinterpret_cast<double*>(smem_raw + lay.offD);
-    unsigned long long* const ckey2 = reinterpret_cast<unsigned long long*>(smem_raw + lay.offKeys);
+    T* const vcand = reinterpret_cast<T*>(smem_raw + Lay::offCand);        // [2][CS][VLEN]
+    T* const Rst = reinterpret_cast<T*>(smem_raw + Lay::offRst);           // [16*CPW][NMAX]
+    T* const taus = reinterpret_cast<T*>(smem_raw + Lay::offTau);
+    T* const stage_v = reinterpret_cast<T*>(smem_raw + Lay::offStageV);                 // [2][VLEN] to be sent
+    unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(smem_raw + Lay::offMbar);
+    double* const dvec = reinterpret_cast<double*>(smem_raw + Lay::offD);
+    double* const bsg = reinterpret_cast<double*>(smem_raw + Lay::offBeta);
+    int* const cpos = reinterpret_cast<int*>(smem_raw + Lay::offPos);
+    unsigned long long* const ckey2 = reinterpret_cast<unsigned long long*>(smem_raw + Lay::offKeys);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int rank = 0;
@@ -225,10 +226,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     // pass / the TMA read from an aligned start
     auto rz_of = [&](int kpos) { return (kpos >= 2 ? kpos - 2 : 0) & ~(EPV - 1); };
     for (int r = tid; r < 2 * VLEN; r += CTA_THREADS) stage_v[r] = mk<T>(0.0);
+    auto xbytes = [&](int kpos) { return (unsigned)(CS * ((n_al - rz_of(kpos)) * sizeof(T) + sizeof(RMeta<T>))); };
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if constexpr (CS > 1) {
+            mbar_expect_tx(&mbar[0], xbytes(0));
+            if (n > 1) mbar_expect_tx(&mbar[1], xbytes(1));
+        }
     }
 
     for (int r = tid; r < 2 * CS * VLEN; r += CTA_THREADS) vcand[r] = mk<T>(0.0);
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     // warp candidate -> shared; block barrier; the warp holding the CTA's best column builds the reflector
     // for position kpos from its registers and pushes it (plus norm, index, tau, beta) to every CTA.
 #ifdef SLA_LDR_TRACE
-#define TR(kk, ev) do { if (p.prof && blockIdx.x == 0 && lane == 0 && (kk) >= 100 && (kk) < 104) p.prof[128 + (((kk) - 100) * 16 + warp) * 12 + (ev)] = clock64(); } while (0)
+#define TR(kk, ev) do { if (p.prof && blockIdx.x < CS && lane == 0 && (kk) >= 100 && (kk) < 104) p.prof[128 + ((((kk) - 100) * CS + rank) * 16 + warp) * 12 + (ev)] = clock64(); } while (0)
 #else
 #define TR(kk, ev) do { } while (0)
 #endif
@@ -401,13 +407,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 #define PROF_MARK(i) do { } while (0)
 #endif
     // ------------------------------------------------------------------ pivoted Householder QR
+    int park_u = -1;   // column of this warp waiting to be parked
     for (int k = 0; k < n; ++k) {
         const int par = k & 1;
         PROF_MARK(0);
         // the ONLY cluster-wide synchronisation per column: wait until all CS candidates have landed here
         if constexpr (CS > 1) {
-            if (tid == 0) mbar_expect_tx(&mbar[par], (unsigned)(CS * ((n_al - rz_of(k)) * sizeof(T) + sizeof(RMeta<T>))));
             mbar_wait(&mbar[par], (unsigned)((k >> 1) & 1));
+            if (tid == 0 && k + 2 < n) mbar_expect_tx(&mbar[par], xbytes(k + 2));   // arm the next phase of this barrier
         } else {
             __syncthreads();
         }
@@ -423,32 +430,41 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         const int pc = key_col(wm.key), plc = pc / CS;
         const T tauk = wm.tau;
         const T* vcur = vcand + ((size_t)par * CS + win) * VLEN;
-        if (tid == 0) { taus[k] = tauk; dvec[k] = fabs(wm.beta); }
-        // ---- the owner warp retires the pivot column: park R'(:, k) in shared memory
+        if (tid == 0) { taus[k] = tauk; dvec[k] = fabs(wm.beta); bsg[k] = wm.beta; }
+        // ---- the owner warp retires the pivot column; it is parked (raw) in shared memory LATER, while the
+        // warp would otherwise idle at the next mbarrier: retired columns are never touched again
         if (rank == win && warp == (plc % CTA_WARPS)) {
-            const int us = plc / CTA_WARPS;
-            T* dst = Rst + (size_t)plc * n;
+            park_u = plc / CTA_WARPS;
+            active &= ~(1u << park_u);
+        }
+        // Deferred duties of column k, done off the critical path (after the pivot scan of column k+1):
+        //  * park the retired column: all RPL row tiles, unmasked; the final pass masks rows >= its position
+        //  * reflector k -> global (rows > k of column k of L) through the TMA, by thread 0 of the CTA that
+        //    won, from its own staging copy (rewritten only after the next block barrier)
+        auto deferred = [&](int kd, bool won) {
+            if (park_u >= 0) {
+                T* dst = Rst + (size_t)(warp + CTA_WARPS * park_u) * NMAX;
 #pragma unroll
-            for (int u = 0; u < CPW; ++u)
-                if (us == u) {
+                for (int u = 0; u < CPW; ++u)
+                    if (park_u == u) {
 #pragma unroll
-                    for (int t = 0; t < RPL; ++t) {
-                        const int r = lane + 32 * t;
-                        if (r < n) dst[r] = (r < k) ? a[u][t] : mk<T>(r == k ? wm.beta : 0.0);
+                        for (int t = 0; t < RPL; ++t) dst[lane + 32 * t] = a[u][t];
                     }
-                }
-            active &= ~(1u << us);   // (its position in A*P is implied by the zero pattern of the parked column)
-        }
-        // reflector k -> global (rows > k of column k of L) through the TMA, by CTA k mod CS
-        if (rank == (k % CS) && k + 1 < n) {
-            const int r0 = (k + 1) & ~(EPV - 1);
-            if (bulk_ok) {
-                if (tid == 0) tma_store(Lg + (long long)k * ldl + r0, vcur + r0, (unsigned)((n - r0) * sizeof(T)));
-            } else {
-                for (int r = k + 1 + tid; r < n; r += CTA_THREADS) Lg[(long long)k * ldl + r] = vcur[r];
+                if (lane == 0) cpos[warp + CTA_WARPS * park_u] = kd;
+                park_u = -1;
             }
-        }
-        if (k == n - 1) break;
+            if (won && kd + 1 < n) {
+                const T* src = (CS > 1) ? stage_v + (size_t)(kd & 1) * VLEN : vcand + (size_t)(kd & 1) * VLEN;
+                const int r0 = (kd + 1) & ~(EPV - 1);
+                if (bulk_ok) {
+                    if (tid == 0) tma_store(Lg + (long long)kd * ldl + r0, src + r0, (unsigned)((n - r0) * sizeof(T)));
+                } else {
+                    for (int r = kd + 1 + tid; r < n; r += CTA_THREADS) Lg[(long long)kd * ldl + r] = src[r];
+                }
+            }
+        };
+        if (k == n - 1) { deferred(k, false); break; }
+        const bool won = (rank == win);
         TR(k, 1);
         PROF_MARK(2);
         // ---- pass (registers only): w = conj(tau) v^H a ; a -= v w ; down-date the squared norms
@@ -469,6 +485,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             v[t] = (lane + 32 * t < n) ? vcur[lane + 32 * t] : mk<T>(0.0);                             \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
             if ((active >> u) & 1u) {                                                                  \
+                SLA_KEEP_BRANCH;                                                                       \
                 T d2_ = mk<T>(0.0);                                                                    \
                 _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                                \
                     fmacc(dot[u], conj_(v[t]), a[u][t]);                                               \
@@ -487,6 +504,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
             ak[u] = shb(ak[u], k & 31) - w[u];                                                         \
             if ((active >> u) & 1u) {                                                                  \
+                SLA_KEEP_BRANCH;                                                                       \
                 _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], w[u]);           \
             }                                                                                          \
         }                                                                                              \
@@ -522,6 +540,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         }
         PROF_MARK(3);
         select_and_publish(k + 1);
+        deferred(k, won);
     }
     PROF_MARK(4);
     if (tid == 0) tma_wait_all();   // all reflectors have landed in global memory
@@ -533,9 +552,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         for (int lc = warp; lc < CTA_WARPS * CPW; lc += CTA_WARPS) {
             const int c = lc * CS + rank;
             if (c >= n) continue;
-            const T* col = Rst + (size_t)lc * n;
+            const T* col = Rst + (size_t)lc * NMAX;
             T* dst = Rg + (long long)c * p.ldr;
-            for (int r = lane; r < n; r += 32) dst[r] = col[r] / dvec[r];   // rows below the pivot position hold 0
+            const int kp = cpos[lc];      // R'(:, kp) = [parked rows < kp ; beta_kp ; 0]
+            const double bk = bsg[kp];
+            for (int r = lane; r < n; r += 32) {
+                const T val = (r < kp) ? col[r] : mk<T>(r == kp ? bk : 0.0);
+                dst[r] = val / dvec[r];
+            }
         }
         if (rank == 0) {
             double* d = p.d + (long long)b * p.stride_d;
@@ -605,6 +629,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         }                                                                                              \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
             if ((qact >> u) & 1u) {                                                                    \
+                SLA_KEEP_BRANCH;                                                                       \
                 T d2_ = mk<T>(0.0);                                                                    \
                 _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                                \
                     fmacc(dot[u], conj_(v[t]), a[u][t]);                                               \
@@ -618,6 +643,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
             const T wu = shb(myw, u * FLS);                                                            \
             if ((qact >> u) & 1u) {                                                                    \
+                SLA_KEEP_BRANCH;                                                                       \
                 _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], wu);             \
             }                                                                                          \
         }                                                                                              \
@@ -656,7 +682,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 // ---- host side --------------------------------------------------------------------------------------
 template <typename T, int CS, int RPL, int CPW> static cudaError_t launch_reg(const LdrArgs<T>& p, cudaStream_t stream) {
     auto kern = ldr_reg_kernel<T, CS, RPL, CPW>;
-    const size_t smem = RegLayout<T, RPL, CPW>(p.n, CS).total;
+    const size_t smem = RegLayout<T, RPL, CPW, CS>::total;
     if (smem > 227 * 1024) return cudaErrorNotSupported;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
