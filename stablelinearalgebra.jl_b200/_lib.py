@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libsla_b200.so")
+# SLA_B200_LIB: another build of the same library (kernel A/B experiments under profiles/); never a fallback
+LIB_PATH = os.environ.get("SLA_B200_LIB") or os.path.join(HERE, "csrc", "libsla_b200.so")
 
 SLA_F64, SLA_C64 = 0, 1
 SLA_OP_N, SLA_OP_C = 0, 1
