@@ -134,7 +134,7 @@ template <typename T> struct Ctx {
             const char* e = getenv("SLA_LDR_ALGO");
             if (getenv("SLA_LDR_STREAMING")) return 3;
             if (!e) return 0;
-            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : 0));
+            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : (e[0] == 'h' ? 4 : 0)));
         }();
         // Cluster kernels minimise latency (one matrix per CS SMs, ~132/CS matrices in flight), the streaming
         // kernel maximises throughput (one matrix per SM, 148 in flight) but is ~4x (register kernel) / ~2.5x
@@ -144,7 +144,18 @@ template <typename T> struct Ctx {
         const int w_stream = waves(batch, 148);
         const bool reg_pays = cs_reg > 0 && waves(batch, 132 / cs_reg) <= 4 * w_stream;
         const bool cl_pays = cs_cl > 0 && 2 * waves(batch, 132 / cs_cl) <= 5 * w_stream;
-        if (forced == 1 ? cs_reg > 0 : (forced == 0 && reg_pays)) CK(ldr_reg_batched<T>(a, s));
+        // 128 < n <= 256, real: the hybrid shape (half the matrix in shared memory, clusters of 2) is ~1.55x slower
+        // per wave than the register kernel but holds twice as many matrices: it wins when it saves waves
+        // (64 chains: 1 wave instead of 2).  SLA_LDR_ALGO=hyb forces it.
+        const int cs_hyb = ldr_hyb_cluster_size<T>(n);
+        bool hyb_pays = false;
+        if (cs_hyb > 0 && forced == 0 && reg_pays) {
+            int c_reg = 0, c_hyb = 0;
+            ldr_n256_resident(&c_reg, &c_hyb);
+            if (c_reg > 0 && c_hyb > 0) hyb_pays = 155 * waves(batch, c_hyb) < 100 * waves(batch, c_reg);
+        }
+        if (cs_hyb > 0 && (forced == 4 || hyb_pays)) CK(ldr_hyb_batched<T>(a, s));
+        else if (forced == 1 ? cs_reg > 0 : (forced == 0 && reg_pays)) CK(ldr_reg_batched<T>(a, s));
         else if (forced == 2 ? cs_cl > 0 : (forced == 0 && cl_pays && cs_reg == 0)) CK(ldr_cluster_batched<T>(a, s));
         else CK(ldr_batched<T>(a, s));
         return 0;

@@ -25,6 +25,10 @@ template <typename T> int ldr_cluster_size(int n);
 // register-resident cluster version for n <= 256, sla_ldr_reg.cu; cluster size 0 = not supported
 template <typename T> cudaError_t ldr_reg_batched(const LdrArgs<T>& p, cudaStream_t s);
 template <typename T> int ldr_reg_cluster_size(int n);
+// hybrid register + shared-memory shape of the same kernel (clusters of 2; real, 128 < n <= 256); 0 = unsupported
+template <typename T> cudaError_t ldr_hyb_batched(const LdrArgs<T>& p, cudaStream_t s);
+template <typename T> int ldr_hyb_cluster_size(int n);
+void ldr_n256_resident(int* reg_clusters, int* hyb_clusters);
 
 // ---- LU / inverse with log|det| and sign (sla_lu.cu) ----------------------------------------
 template <typename T> struct LuArgs {

@@ -48,7 +48,7 @@ template <typename T> struct alignas(16) RMeta {   // 32 bytes for both element 
 
 // Shared-memory layout, fixed at compile time (sized for NMAX, not n) so that every address in the per-column
 // chain is base + immediate.
-template <typename T, int RPL, int CPW, int CS> struct RegLayout {
+template <typename T, int RPL, int CPW, int CS, int SPW> struct RegLayout {
     static constexpr int NMAX = 32 * RPL;
     static constexpr int VLEN = NMAX + 8;
     static constexpr size_t al16(size_t o) { return (o + 15) & ~(size_t)15; }
@@ -57,14 +57,16 @@ template <typename T, int RPL, int CPW, int CS> struct RegLayout {
     static constexpr size_t candBytes = 2 * (size_t)CS * VLEN * sizeof(T), ringBytes = 2 * (size_t)QKC_R * NMAX * sizeof(T);
     static constexpr size_t offCand = 0;
     static constexpr size_t offRst = offCand + (candBytes > ringBytes ? candBytes : ringBytes);   // parked (raw) pivot columns [lc][NMAX]
-    static constexpr size_t offTau = offRst + (size_t)CTA_WARPS * CPW * NMAX * sizeof(T);
+    // SPW == 0: parking area for retired register columns.  SPW > 0 (hybrid): the shared-memory resident columns
+    // [warp][SPW][RPL/2][32 lanes][2] (thread-private, 16-byte pairs); retired register columns go to global R
+    static constexpr size_t offTau = offRst + (size_t)CTA_WARPS * (SPW > 0 ? SPW : CPW) * NMAX * sizeof(T);
     static constexpr size_t offStageV = al16(offTau + (size_t)NMAX * sizeof(T));   // [2][VLEN] staging of the published candidate
     static constexpr size_t offMbar = offStageV + 2 * (size_t)VLEN * sizeof(T);    // one mbarrier per column parity
     static constexpr size_t offD = al16(offMbar + 2 * sizeof(unsigned long long));
     static constexpr size_t offBeta = offD + (size_t)NMAX * sizeof(double);        // signed beta_k = R'(k, pivot column k)
     static constexpr size_t offKeys = al16(offBeta + (size_t)NMAX * sizeof(double));   // [2][16*CPW] pivot keys
-    static constexpr size_t offPos = offKeys + 2 * (size_t)CTA_WARPS * CPW * sizeof(unsigned long long);   // pivot position per local column
-    static constexpr size_t total = offPos + (size_t)CTA_WARPS * CPW * sizeof(int) + 64;
+    static constexpr size_t offPos = offKeys + 2 * (size_t)CTA_WARPS * (CPW + SPW) * sizeof(unsigned long long);   // pivot position per local column
+    static constexpr size_t total = offPos + (size_t)CTA_WARPS * (CPW + SPW) * sizeof(int) + 64;
 };
 
 template <int CS> __device__ __forceinline__ void cl_barrier() {
@@ -158,17 +160,26 @@ __device__ __forceinline__ void dsmem_bulk_copy(void* dst_local_addr, const void
 
 }  // namespace
 
-template <typename T, int CS, int RPL, int CPW>
+// SPW > 0 is the HYBRID shape: besides its CPW register columns a warp owns SPW columns that live in shared
+// memory (thread-private layout: a lane only ever touches its own rows), so that a matrix needs half as many
+// SMs and twice as many matrices are resident -- one wave instead of two for 64 chains of N = 256.
+template <typename T, int CS, int RPL, int CPW, int SPW>
 __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
-    using Lay = RegLayout<T, RPL, CPW, CS>;
+    using Lay = RegLayout<T, RPL, CPW, CS, SPW>;
     constexpr int NMAX = Lay::NMAX, VLEN = Lay::VLEN;
-    constexpr int FLS = 32 / CPW;                 // lanes per lane-group; lane u*FLS leads column u of the warp
+    constexpr int TOT = CPW + SPW;                // columns per warp (register + shared)
+    constexpr int FLS = 32 / TOT;                 // lanes per lane-group; lane u*FLS leads column u of the warp
     constexpr bool CP = is_cplx<T>::value;
+    static_assert(SPW == 0 || (!CP && RPL % 2 == 0), "hybrid shape: real only");
     constexpr int EPV = CP ? 1 : 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n;
     T* const vcand = reinterpret_cast<T*>(smem_raw + Lay::offCand);        // [2][CS][VLEN]
-    T* const Rst = reinterpret_cast<T*>(smem_raw + Lay::offRst);           // [16*CPW][NMAX]
+    T* const Rst = reinterpret_cast<T*>(smem_raw + Lay::offRst);           // [16*CPW][NMAX]   (SPW == 0)
+    // hybrid: element (su, t) of this lane at scol[(su*RPL/2 + t/2)*64 + (t&1)]  (16-byte pairs of row tiles)
+    T* const scol = Rst + ((size_t)(threadIdx.x >> 5) * (SPW > 0 ? SPW : 1) * RPL * 32) + (threadIdx.x & 31) * 2;
+    auto sld = [&](int su, int t) -> T { return scol[(su * (RPL / 2) + (t >> 1)) * 64 + (t & 1)]; };
+    auto sst = [&](int su, int t, T v) { scol[(su * (RPL / 2) + (t >> 1)) * 64 + (t & 1)] = v; };
     T* const taus = reinterpret_cast<T*>(smem_raw + Lay::offTau);
     T* const stage_v = reinterpret_cast<T*>(smem_raw + Lay::offStageV);                 // [2][VLEN] to be sent
     unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(smem_raw + Lay::offMbar);
@@ -191,35 +202,33 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     // column u of this warp: local index lc = warp + 16 u, global c = lc*CS + rank
     T a[CPW][RPL];
     unsigned active = 0;
-    double ssq[CPW];
+    double ssq[TOT];
 #pragma unroll
-    for (int u = 0; u < CPW; ++u) {
+    for (int u = 0; u < TOT; ++u) {
         const int c = (warp + CTA_WARPS * u) * CS + rank;
         ssq[u] = 0.0;
-        if (c < n) {
-            active |= 1u << u;
-            const T* src = Ain + (long long)c * ldin;
+        if (c < n) active |= 1u << u;
+        const T* src = Ain + (long long)c * ldin;
 #pragma unroll
-            for (int t = 0; t < RPL; ++t) {
-                const int r = lane + 32 * t;
-                a[u][t] = (r < n) ? src[r] : mk<T>(0.0);
-                ssq[u] += abs2_(a[u][t]);
-            }
-        } else {
-#pragma unroll
-            for (int t = 0; t < RPL; ++t) a[u][t] = mk<T>(0.0);
+        for (int t = 0; t < RPL; ++t) {
+            const int r = lane + 32 * t;
+            const T val = (c < n && r < n) ? src[r] : mk<T>(0.0);
+            ssq[u] += abs2_(val);
+            if (u < CPW) a[u < CPW ? u : 0][t] = val;
+            else sst(u - CPW, t, val);
         }
     }
-    // squared partial norms live in the lane-group leaders' registers
+    // squared partial column norms, replicated in every lane of the column's lane group (no divergence in the
+    // down-dating): vn1 = current estimate, rvn1 = 1/vn1, q12 = vn1 / (value at the last exact computation)
     const int myu = lane / FLS;
     const bool leader = (lane % FLS) == 0;
-    double vn1 = reduce_transposed<double, CPW>(ssq, lane);
-    double ivn2 = 1.0 / vn1;   // 1 / (squared norm at the last exact computation)
+    double vn1 = reduce_transposed<double, TOT>(ssq, lane);
+    double rvn1 = 1.0 / vn1, q12 = 1.0;
     const int myc = (warp + CTA_WARPS * myu) * CS + rank;
     const int n_al = (n + EPV - 1) & ~(EPV - 1);
-    constexpr int NKEY = CTA_WARPS * CPW;   // one key slot per (warp, column)
+    constexpr int NKEY = CTA_WARPS * TOT;   // one key slot per (warp, column)
     constexpr int KPL = NKEY / 32;          // keys a lane scans
-    static_assert(CPW == 2 || CPW == 4 || CPW == 8, "CPW");
+    static_assert(TOT == 2 || TOT == 4 || TOT == 8, "columns per warp");
     // the RMeta of a candidate travels right behind its vector (one bulk copy per peer)
     auto slot_meta = [&](T* slot) { return reinterpret_cast<RMeta<T>*>(slot + n_al); };
     // rows [rz, kpos) of a candidate are written as zeros: the slot still holds an older vector there and the
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 #endif
         const int par = kpos & 1;
         unsigned long long* const ckey = ckey2 + par * NKEY;
-        if (leader) ckey[warp * CPW + myu] = ((active >> myu) & 1u) ? pack_key(vn1, myc) : 0ull;
+        if (leader) ckey[warp * TOT + myu] = ((active >> myu) & 1u) ? pack_key(vn1, myc) : 0ull;
         TR(kpos - 1, 5);
         if (tid == 0) tma_wait_read();   // the TMA finished reading the slot that peers may overwrite from now on
         if (warp == 0) SP_MARK(0);   // key store
@@ -317,6 +326,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) x[t] = a[u][t];
             }
+        if constexpr (SPW > 0) {
+            if (ub >= CPW) {
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) x[t] = sld(ub - CPW, t);
+            }
+        }
         double sq_[RPL];
         T xk = mk<T>(0.0);
         const int tk = kpos >> 5;
@@ -443,13 +458,25 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         //    won, from its own staging copy (rewritten only after the next block barrier)
         auto deferred = [&](int kd, bool won) {
             if (park_u >= 0) {
-                T* dst = Rst + (size_t)(warp + CTA_WARPS * park_u) * NMAX;
+                if constexpr (SPW == 0) {
+                    T* dst = Rst + (size_t)(warp + CTA_WARPS * park_u) * NMAX;
 #pragma unroll
-                for (int u = 0; u < CPW; ++u)
-                    if (park_u == u) {
+                    for (int u = 0; u < CPW; ++u)
+                        if (park_u == u) {
 #pragma unroll
-                        for (int t = 0; t < RPL; ++t) dst[lane + 32 * t] = a[u][t];
-                    }
+                            for (int t = 0; t < RPL; ++t) dst[lane + 32 * t] = a[u][t];
+                        }
+                } else if (park_u < CPW) {
+                    // hybrid: a retired register column goes (raw) to its column of R in global memory; the final
+                    // pass re-reads it with the same lane <-> row mapping.  Shared columns simply stay where they are.
+                    T* dst = p.R + (long long)b * p.strideR + (long long)((warp + CTA_WARPS * park_u) * CS + rank) * p.ldr;
+#pragma unroll
+                    for (int u = 0; u < CPW; ++u)
+                        if (park_u == u) {
+#pragma unroll
+                            for (int t = 0; t < RPL; ++t) if (lane + 32 * t < n) dst[lane + 32 * t] = a[u][t];
+                        }
+                }
                 if (lane == 0) cpos[warp + CTA_WARPS * park_u] = kd;
                 park_u = -1;
             }
@@ -467,15 +494,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         const bool won = (rank == win);
         TR(k, 1);
         PROF_MARK(2);
-        // ---- pass (registers only): w = conj(tau) v^H a ; a -= v w ; down-date the squared norms
+        // ---- pass: w = conj(tau) v^H a ; a -= v w ; down-date the squared norms.  Register columns never leave
+        // the registers; the shared columns of the hybrid shape stream through 16-byte thread-private loads/stores
+        double temp = 1.0;
         if (active) {
             const int tlo = k >> 5;   // row tiles below this hold only rows < k: v is zero there -> skipped
             T v[RPL];
-            T dot[CPW];
-            T w[CPW];
-            T ak[CPW];
+            T dot[TOT];
+            T akm = mk<T>(0.0);       // element (k, column myu) before the update
 #pragma unroll
-            for (int u = 0; u < CPW; ++u) { dot[u] = mk<T>(0.0); ak[u] = mk<T>(0.0); }
+            for (int u = 0; u < TOT; ++u) dot[u] = mk<T>(0.0);
+            T myw;
             // straight-line code (all loads first, full ILP) over the row tiles [T0, RPL), one variant per
             // pair of tiles so that tiles holding only rows < k are skipped; retired columns are skipped too
             // (warp-uniform branches), so the FP64 work shrinks with the active (n-k) x (n-k) block
@@ -483,6 +512,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     {                                                                                                  \
         _Pragma("unroll") for (int t = (T0); t < RPL; ++t)                                             \
             v[t] = (lane + 32 * t < n) ? vcur[lane + 32 * t] : mk<T>(0.0);                             \
+        _Pragma("unroll") for (int t = (T0); t < RPL && t < (T0) + 2; ++t)                             \
+            if (t == tlo) {                                                                            \
+                _Pragma("unroll") for (int u = 0; u < TOT; ++u) {                                      \
+                    T e_;                                                                              \
+                    if constexpr (SPW > 0) e_ = (u < CPW) ? a[u < CPW ? u : 0][t] : sld(u - CPW, t);   \
+                    else e_ = a[u < CPW ? u : 0][t];                                                   \
+                    e_ = shb(e_, k & 31);                                                              \
+                    if (myu == u) akm = e_;                                                            \
+                }                                                                                      \
+            }                                                                                          \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
             if ((active >> u) & 1u) {                                                                  \
                 SLA_KEEP_BRANCH;                                                                       \
@@ -494,18 +533,43 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                 dot[u] = dot[u] + d2_;                                                                 \
             }                                                                                          \
         }                                                                                              \
+        if constexpr (SPW > 0) {                                                                       \
+            _Pragma("unroll") for (int su = 0; su < SPW; ++su) {                                       \
+                if ((active >> (CPW + su)) & 1u) {                                                     \
+                    SLA_KEEP_BRANCH;                                                                   \
+                    double d2_ = 0.0;                                                                  \
+                    _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                            \
+                        const double2 x2_ = *reinterpret_cast<const double2*>(&scol[(su * (RPL / 2) + (t >> 1)) * 64]); \
+                        dot[CPW + su] = fma(real_(v[t]), x2_.x, real_(dot[CPW + su]));                 \
+                        d2_ = fma(real_(v[t + 1]), x2_.y, d2_);                                        \
+                    }                                                                                  \
+                    dot[CPW + su] = dot[CPW + su] + mk<T>(d2_);                                        \
+                }                                                                                      \
+            }                                                                                          \
+        }                                                                                              \
         TR(k, 2);                                                                                      \
-        const T mydot = reduce_transposed<T, CPW>(dot, lane);                                          \
-        const T myw = conj_(tauk) * mydot;                                                             \
+        myw = conj_(tauk) * reduce_transposed<T, TOT>(dot, lane);                                      \
         TR(k, 3);                                                                                      \
-        _Pragma("unroll") for (int u = 0; u < CPW; ++u) w[u] = shb(myw, u * FLS);                      \
-        _Pragma("unroll") for (int t = (T0); t < RPL && t < (T0) + 2; ++t)                             \
-            if (t == tlo) { _Pragma("unroll") for (int u = 0; u < CPW; ++u) ak[u] = a[u][t]; }         \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
-            ak[u] = shb(ak[u], k & 31) - w[u];                                                         \
+            const T wu = shb(myw, u * FLS);                                                            \
             if ((active >> u) & 1u) {                                                                  \
                 SLA_KEEP_BRANCH;                                                                       \
-                _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], w[u]);           \
+                _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], wu);             \
+            }                                                                                          \
+        }                                                                                              \
+        if constexpr (SPW > 0) {                                                                       \
+            _Pragma("unroll") for (int su = 0; su < SPW; ++su) {                                       \
+                const double wu = real_(shb(myw, (CPW + su) * FLS));                                   \
+                if ((active >> (CPW + su)) & 1u) {                                                     \
+                    SLA_KEEP_BRANCH;                                                                   \
+                    _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                            \
+                        double2* q_ = reinterpret_cast<double2*>(&scol[(su * (RPL / 2) + (t >> 1)) * 64]); \
+                        double2 x2_ = *q_;                                                             \
+                        x2_.x = fma(-real_(v[t]), wu, x2_.x);                                          \
+                        x2_.y = fma(-real_(v[t + 1]), wu, x2_.y);                                      \
+                        *q_ = x2_;                                                                     \
+                    }                                                                                  \
+                }                                                                                      \
             }                                                                                          \
         }                                                                                              \
     }
@@ -515,18 +579,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             else SLA_PASS(0)
 #undef SLA_PASS
             TR(k, 4);
+            // element (k, column myu) after the update is a_k - w (v_k = 1): down-date the squared norm
+            const bool cond = ((active >> myu) & 1u) && vn1 != 0.0;
             bool flagged = false;
-            if (leader && ((active >> myu) & 1u) && vn1 != 0.0) {
-                const T akm = pickv<T, CPW>(ak, myu);
-                const double temp = fmax(0.0, fma(-abs2_(akm), __drcp_rn(vn1), 1.0));
-                if (temp * (vn1 * ivn2) <= TOL3Z_R) flagged = true;
-                else vn1 *= temp;
+            if (cond) {
+                temp = fmax(0.0, fma(-abs2_(akm - myw), rvn1, 1.0));
+                flagged = temp * q12 <= TOL3Z_R;
+                if (!flagged) vn1 *= temp;
             }
             unsigned fl = __ballot_sync(0xffffffffu, flagged);
-            while (fl) {   // exact squared norm of a flagged column below row k, straight from the registers
-                const int src = __ffs(fl) - 1;
-                fl &= fl - 1;
-                const int uf = src / FLS;
+            while (fl) {   // exact squared norm of a flagged (already updated) column below row k
+                const int uf = (__ffs(fl) - 1) / FLS;
+                fl &= ~((FLS == 32 ? 0xffffffffu : ((1u << FLS) - 1u)) << (uf * FLS));
                 double ss = 0.0;
 #pragma unroll
                 for (int u = 0; u < CPW; ++u)
@@ -534,12 +598,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 #pragma unroll
                         for (int t = 0; t < RPL; ++t) if (lane + 32 * t > k) ss += abs2_(a[u][t]);
                     }
+                if constexpr (SPW > 0) {
+                    if (uf >= CPW) {
+#pragma unroll
+                        for (int t = 0; t < RPL; ++t) if (lane + 32 * t > k) ss += abs2_(sld(uf - CPW, t));
+                    }
+                }
                 ss = warp_sum(ss);
-                if (lane == src) { vn1 = ss; ivn2 = 1.0 / ss; }
+                if (myu == uf) { vn1 = ss; q12 = 1.0; temp = 1.0; }
             }
         }
         PROF_MARK(3);
         select_and_publish(k + 1);
+        // off the critical path: the ratio and reciprocal the next down-dating needs, then the deferred duties
+        q12 *= temp;
+        rvn1 = 1.0 / vn1;
         deferred(k, won);
     }
     PROF_MARK(4);
@@ -549,15 +622,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     // ------------------------------------------------------------------ d, R (original column order)
     {
         T* Rg = p.R + (long long)b * p.strideR;
-        for (int lc = warp; lc < CTA_WARPS * CPW; lc += CTA_WARPS) {
+#pragma unroll
+        for (int u = 0; u < TOT; ++u) {   // the warp's own columns, same lane <-> row mapping as the parking
+            const int lc = warp + CTA_WARPS * u;
             const int c = lc * CS + rank;
             if (c >= n) continue;
-            const T* col = Rst + (size_t)lc * NMAX;
             T* dst = Rg + (long long)c * p.ldr;
             const int kp = cpos[lc];      // R'(:, kp) = [parked rows < kp ; beta_kp ; 0]
             const double bk = bsg[kp];
-            for (int r = lane; r < n; r += 32) {
-                const T val = (r < kp) ? col[r] : mk<T>(r == kp ? bk : 0.0);
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) {
+                const int r = lane + 32 * t;
+                if (r >= n) continue;
+                T raw;
+                if constexpr (SPW == 0) raw = Rst[(size_t)lc * NMAX + r];
+                else raw = (u < CPW) ? dst[r] : sld(u - CPW, t);
+                const T val = (r < kp) ? raw : mk<T>(r == kp ? bk : 0.0);
                 dst[r] = val / dvec[r];
             }
         }
@@ -571,11 +651,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     PROF_MARK(5);
 
     // ------------------------------------------------------------------ Q = H_0 ... H_{n-1} applied to I
+    // Column c of Q is touched by the reflectors k <= c only: in the hybrid shape the register slots take the
+    // HIGH columns (most work) and the shared-memory slots the low ones, which wake up last
+    auto qcol = [&](int u) { return (warp + CTA_WARPS * ((u + SPW) % TOT)) * CS + rank; };
 #pragma unroll
-    for (int u = 0; u < CPW; ++u) {
-        const int c = (warp + CTA_WARPS * u) * CS + rank;
+    for (int u = 0; u < TOT; ++u) {
+        const int c = qcol(u);
 #pragma unroll
-        for (int t = 0; t < RPL; ++t) a[u][t] = mk<T>((lane + 32 * t == c && c < n) ? 1.0 : 0.0);
+        for (int t = 0; t < RPL; ++t) {
+            const T e = mk<T>((lane + 32 * t == c && c < n) ? 1.0 : 0.0);
+            if (u < CPW) a[u < CPW ? u : 0][t] = e;
+            else sst(u - CPW, t, e);
+        }
     }
     {
         T* const ring = vcand;   // [2][QKC][NMAX]
@@ -607,8 +694,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             // columns left of the whole chunk are untouched by it
             unsigned qact = 0;
 #pragma unroll
-            for (int u = 0; u < CPW; ++u) {
-                const int c = (warp + CTA_WARPS * u) * CS + rank;
+            for (int u = 0; u < TOT; ++u) {
+                const int c = qcol(u);
                 if ((c < n) && (c >= k0)) qact |= 1u << u;
             }
             if (qact) {
@@ -618,9 +705,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                     const T* vk = vb + (size_t)i * NMAX;
                     const T tk = taus[k];
                     T v[RPL];
-                    T dot[CPW];
+                    T dot[TOT];
 #pragma unroll
-                    for (int u = 0; u < CPW; ++u) dot[u] = mk<T>(0.0);
+                    for (int u = 0; u < TOT; ++u) dot[u] = mk<T>(0.0);
 #define SLA_QPASS(T0)                                                                                  \
     {                                                                                                  \
         _Pragma("unroll") for (int t = (T0); t < RPL; ++t) {                                           \
@@ -638,13 +725,42 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                 dot[u] = dot[u] + d2_;                                                                 \
             }                                                                                          \
         }                                                                                              \
-        const T mydot = reduce_transposed<T, CPW>(dot, lane);                                          \
+        if constexpr (SPW > 0) {                                                                       \
+            _Pragma("unroll") for (int su = 0; su < SPW; ++su) {                                       \
+                if ((qact >> (CPW + su)) & 1u) {                                                       \
+                    SLA_KEEP_BRANCH;                                                                   \
+                    double d2_ = 0.0;                                                                  \
+                    _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                            \
+                        const double2 x2_ = *reinterpret_cast<const double2*>(&scol[(su * (RPL / 2) + (t >> 1)) * 64]); \
+                        dot[CPW + su] = fma(real_(v[t]), x2_.x, real_(dot[CPW + su]));                 \
+                        d2_ = fma(real_(v[t + 1]), x2_.y, d2_);                                        \
+                    }                                                                                  \
+                    dot[CPW + su] = dot[CPW + su] + mk<T>(d2_);                                        \
+                }                                                                                      \
+            }                                                                                          \
+        }                                                                                              \
+        const T mydot = reduce_transposed<T, TOT>(dot, lane);                                          \
         const T myw = tk * mydot;                                                                      \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
             const T wu = shb(myw, u * FLS);                                                            \
             if ((qact >> u) & 1u) {                                                                    \
                 SLA_KEEP_BRANCH;                                                                       \
                 _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], wu);             \
+            }                                                                                          \
+        }                                                                                              \
+        if constexpr (SPW > 0) {                                                                       \
+            _Pragma("unroll") for (int su = 0; su < SPW; ++su) {                                       \
+                const double wu = real_(shb(myw, (CPW + su) * FLS));                                   \
+                if ((qact >> (CPW + su)) & 1u) {                                                       \
+                    SLA_KEEP_BRANCH;                                                                   \
+                    _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                            \
+                        double2* q_ = reinterpret_cast<double2*>(&scol[(su * (RPL / 2) + (t >> 1)) * 64]); \
+                        double2 x2_ = *q_;                                                             \
+                        x2_.x = fma(-real_(v[t]), wu, x2_.x);                                          \
+                        x2_.y = fma(-real_(v[t + 1]), wu, x2_.y);                                      \
+                        *q_ = x2_;                                                                     \
+                    }                                                                                  \
+                }                                                                                      \
             }                                                                                          \
         }                                                                                              \
     }
@@ -666,23 +782,26 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 #endif
 #undef PROF_MARK
 #pragma unroll
-    for (int u = 0; u < CPW; ++u) {
-        const int c = (warp + CTA_WARPS * u) * CS + rank;
+    for (int u = 0; u < TOT; ++u) {
+        const int c = qcol(u);
         if (c < n) {
             T* dst = Lg + (long long)c * ldl;
 #pragma unroll
             for (int t = 0; t < RPL; ++t) {
                 const int r = lane + 32 * t;
-                if (r < n) dst[r] = a[u][t];
+                if (r < n) {
+                    if (u < CPW) dst[r] = a[u < CPW ? u : 0][t];
+                    else dst[r] = sld(u - CPW, t);
+                }
             }
         }
     }
 }
 
 // ---- host side --------------------------------------------------------------------------------------
-template <typename T, int CS, int RPL, int CPW> static cudaError_t launch_reg(const LdrArgs<T>& p, cudaStream_t stream) {
-    auto kern = ldr_reg_kernel<T, CS, RPL, CPW>;
-    const size_t smem = RegLayout<T, RPL, CPW, CS>::total;
+template <typename T, int CS, int RPL, int CPW, int SPW = 0> static cudaError_t launch_reg(const LdrArgs<T>& p, cudaStream_t stream) {
+    auto kern = ldr_reg_kernel<T, CS, RPL, CPW, SPW>;
+    const size_t smem = RegLayout<T, RPL, CPW, CS, SPW>::total;
     if (smem > 227 * 1024) return cudaErrorNotSupported;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -701,6 +820,27 @@ template <typename T, int CS, int RPL, int CPW> static cudaError_t launch_reg(co
     e = cudaLaunchKernelEx(&cfg, kern, p);
     ++g_launch_count;
     return e;
+}
+
+// how many clusters of this shape the device holds at once (GPC fragmentation included); cached by the callers
+template <typename T, int CS, int RPL, int CPW, int SPW = 0> static int max_clusters_of() {
+    auto kern = ldr_reg_kernel<T, CS, RPL, CPW, SPW>;
+    const size_t smem = RegLayout<T, RPL, CPW, CS, SPW>::total;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS * 64, 1, 1);
+    cfg.blockDim = dim3(CTA_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return nc;
 }
 
 // register tile shapes: real 32 doubles per lane, complex 16 complex per lane
@@ -729,6 +869,22 @@ template <> cudaError_t ldr_reg_batched<cplx>(const LdrArgs<cplx>& p, cudaStream
     if (p.n <= 128) return launch_reg<cplx, 2, 4, 4>(p, s);
     if (p.n <= 256) return launch_reg<cplx, 8, 8, 2>(p, s);
     return cudaErrorNotSupported;
+}
+
+// ---- hybrid shape (real, 128 < n <= 256): clusters of 2, half of the matrix in registers, half in shared memory
+template <> cudaError_t ldr_hyb_batched<double>(const LdrArgs<double>& p, cudaStream_t s) {
+    if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
+    if (p.n > 256) return cudaErrorNotSupported;
+    return launch_reg<double, 2, 8, 4, 4>(p, s);
+}
+template <> cudaError_t ldr_hyb_batched<cplx>(const LdrArgs<cplx>&, cudaStream_t) { return cudaErrorNotSupported; }
+template <> int ldr_hyb_cluster_size<double>(int n) { return (n > 128 && n <= 256) ? 2 : 0; }
+template <> int ldr_hyb_cluster_size<cplx>(int) { return 0; }
+// resident matrices of the N <= 256 real shapes: {register kernel (clusters of 4), hybrid (clusters of 2)}
+void ldr_n256_resident(int* reg_clusters, int* hyb_clusters) {
+    static const int r = max_clusters_of<double, 4, 8, 4>(), h = max_clusters_of<double, 2, 8, 4, 4>();
+    *reg_clusters = r;
+    *hyb_clusters = h;
 }
 
 template int ldr_reg_cluster_size<double>(int);
