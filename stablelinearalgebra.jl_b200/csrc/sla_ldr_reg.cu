@@ -200,12 +200,20 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 
     // ------------------------------------------------------------------ load: columns -> registers
     // column u of this warp: local index lc = warp + 16 u, global c = lc*CS + rank
+    // Slot u of a warp (u < CPW: registers, else shared memory) holds local column lc = warp + 16 * grp(u), global
+    // c = lc*CS + rank.  In the hybrid shape the SHARED slots take the low column groups: a DQMC chain hands
+    // over (B L) D with D sorted descending, so the low columns are pivoted (retired) first and the shared-memory
+    // traffic dies out early; for Q = H_0...H_{n-1} I the low columns wake up last.  Any input is handled, this
+    // only decides which half is the cheaper one.
+    auto grp = [&](int u) { return (u + SPW) % TOT; };
+    auto slot_of_grp = [&](int g) { return (g + CPW) % TOT; };
+    auto colof = [&](int u) { return (warp + CTA_WARPS * grp(u)) * CS + rank; };
     T a[CPW][RPL];
     unsigned active = 0;
     double ssq[TOT];
 #pragma unroll
     for (int u = 0; u < TOT; ++u) {
-        const int c = (warp + CTA_WARPS * u) * CS + rank;
+        const int c = colof(u);
         ssq[u] = 0.0;
         if (c < n) active |= 1u << u;
         const T* src = Ain + (long long)c * ldin;
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     const bool leader = (lane % FLS) == 0;
     double vn1 = reduce_transposed<double, TOT>(ssq, lane);
     double rvn1 = 1.0 / vn1, q12 = 1.0;
-    const int myc = (warp + CTA_WARPS * myu) * CS + rank;
+    const int myc = colof(myu);
     const int n_al = (n + EPV - 1) & ~(EPV - 1);
     constexpr int NKEY = CTA_WARPS * TOT;   // one key slot per (warp, column)
     constexpr int KPL = NKEY / 32;          // keys a lane scans
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         const int ci = key_col(ck);
         const int clc = ci / CS;
         if (warp != (clc % CTA_WARPS)) return;
-        const int ub = clc / CTA_WARPS;   // which of my columns
+        const int ub = slot_of_grp(clc / CTA_WARPS);   // which of my columns
         SP_MARK(2);   // (winner warp) key scan
         T x[RPL];
 #pragma unroll
@@ -449,7 +457,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         // ---- the owner warp retires the pivot column; it is parked (raw) in shared memory LATER, while the
         // warp would otherwise idle at the next mbarrier: retired columns are never touched again
         if (rank == win && warp == (plc % CTA_WARPS)) {
-            park_u = plc / CTA_WARPS;
+            park_u = slot_of_grp(plc / CTA_WARPS);
             active &= ~(1u << park_u);
         }
         // Deferred duties of column k, done off the critical path (after the pivot scan of column k+1):
@@ -469,7 +477,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                 } else if (park_u < CPW) {
                     // hybrid: a retired register column goes (raw) to its column of R in global memory; the final
                     // pass re-reads it with the same lane <-> row mapping.  Shared columns simply stay where they are.
-                    T* dst = p.R + (long long)b * p.strideR + (long long)((warp + CTA_WARPS * park_u) * CS + rank) * p.ldr;
+                    T* dst = p.R + (long long)b * p.strideR + (long long)colof(park_u) * p.ldr;
 #pragma unroll
                     for (int u = 0; u < CPW; ++u)
                         if (park_u == u) {
@@ -624,8 +632,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         T* Rg = p.R + (long long)b * p.strideR;
 #pragma unroll
         for (int u = 0; u < TOT; ++u) {   // the warp's own columns, same lane <-> row mapping as the parking
-            const int lc = warp + CTA_WARPS * u;
-            const int c = lc * CS + rank;
+            const int lc = warp + CTA_WARPS * u;   // slot index (parking area, cpos)
+            const int c = colof(u);
             if (c >= n) continue;
             T* dst = Rg + (long long)c * p.ldr;
             const int kp = cpos[lc];      // R'(:, kp) = [parked rows < kp ; beta_kp ; 0]
@@ -651,12 +659,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     PROF_MARK(5);
 
     // ------------------------------------------------------------------ Q = H_0 ... H_{n-1} applied to I
-    // Column c of Q is touched by the reflectors k <= c only: in the hybrid shape the register slots take the
-    // HIGH columns (most work) and the shared-memory slots the low ones, which wake up last
-    auto qcol = [&](int u) { return (warp + CTA_WARPS * ((u + SPW) % TOT)) * CS + rank; };
+    // (column c of Q is touched by the reflectors k <= c only: the shared slots hold the low columns, see colof)
 #pragma unroll
     for (int u = 0; u < TOT; ++u) {
-        const int c = qcol(u);
+        const int c = colof(u);
 #pragma unroll
         for (int t = 0; t < RPL; ++t) {
             const T e = mk<T>((lane + 32 * t == c && c < n) ? 1.0 : 0.0);
@@ -695,7 +701,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             unsigned qact = 0;
 #pragma unroll
             for (int u = 0; u < TOT; ++u) {
-                const int c = qcol(u);
+                const int c = colof(u);
                 if ((c < n) && (c >= k0)) qact |= 1u << u;
             }
             if (qact) {
@@ -783,7 +789,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 #undef PROF_MARK
 #pragma unroll
     for (int u = 0; u < TOT; ++u) {
-        const int c = qcol(u);
+        const int c = colof(u);
         if (c < n) {
             T* dst = Lg + (long long)c * ldl;
 #pragma unroll

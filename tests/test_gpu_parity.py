@@ -522,7 +522,16 @@ def test_full_size_properties_C2(S):
     assert np.isfinite(Gh).all()
 
 
-@pytest.mark.parametrize("algo", ["streaming", "cluster"])
+@pytest.mark.parametrize("n", [130, 200, 255, 256])
+def test_ldr_hybrid_shape(S, n):
+    """More than one wave of register-kernel clusters (batch > 33) at 128 < n <= 256 selects the hybrid register +
+    shared-memory shape of the LDR kernel (clusters of 2): same checks, random and strongly graded columns."""
+    rng = np.random.default_rng(100 + n)
+    A = np.concatenate([rand_matrix(rng, n, False, 18), graded_matrix(rng, n, False, 80, 18)])
+    check_ldr(S, A)
+
+
+@pytest.mark.parametrize("algo", ["streaming", "cluster", "hyb"])
 def test_other_ldr_kernels_subprocess(algo):
     """Default LDR kernel for n <= 256 is the register-resident cluster kernel.  The shared-memory cluster
     kernel (256 < n <= 512, e.g. C5's N=400) and the L2-streaming kernel (larger n, e.g. C4's N=1024) are
