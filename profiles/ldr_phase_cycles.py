@@ -6,7 +6,9 @@ import sla_b200 as sla
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 rng = np.random.default_rng(0)
-A = rng.standard_normal((batch, n, n)) * (10.0 ** rng.uniform(-40, 40, size=(batch, 1, n)))
+graded = len(sys.argv) > 3 and sys.argv[3] == "graded"   # DQMC-like: column scales sorted descending
+A = rng.standard_normal((batch, n, n)) * ((10.0 ** np.linspace(20, -20, n))[None, None, :] if graded
+                                          else 10.0 ** rng.uniform(-40, 40, size=(batch, 1, n)))
 dA = sla.to_device(A)
 ws = sla.ldr_workspace(dA)
 F = sla.ldr(dA)

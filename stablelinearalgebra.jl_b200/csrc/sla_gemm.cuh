@@ -102,7 +102,9 @@ __device__ __forceinline__ void mma_tile(cplx (&acc)[2], cplx nf, cplx mf) {
 }
 
 template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES, bool VEC>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 1) gemm_kernel(GemmArgs<T> p) {
+// 64x64 real tiles: cap the registers at 128 so that 4 CTAs (not 3) are resident per SM -- fewer, fuller waves for the
+// 1024-2048 CTA launches of a 64-128 chain batch
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (sizeof(T) == 8 && BM * BN <= 64 * 64) ? 4 : 1) gemm_kernel(GemmArgs<T> p) {
     constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
     constexpr int NT = WARPS_M * WARPS_N * 32;
     constexpr int MF = WM / 8, NF = WN / 8;
