@@ -163,7 +163,10 @@ __device__ __forceinline__ void dsmem_bulk_copy(void* dst_local_addr, const void
 // SPW > 0 is the HYBRID shape: besides its CPW register columns a warp owns SPW columns that live in shared
 // memory (thread-private layout: a lane only ever touches its own rows), so that a matrix needs half as many
 // SMs and twice as many matrices are resident -- one wave instead of two for 64 chains of N = 256.
-template <typename T, int CS, int RPL, int CPW, int SPW>
+// MODE 0: factorisation + Q formation in one launch.  MODE 1: factorisation only (reflectors -> L, taus -> p.Twork).
+// MODE 2: Q formation only, from the reflectors and taus a MODE 1 launch left behind -- used to form Q with the
+// register shape (4 SMs per matrix, no shared-memory half) after the hybrid shape has factorised in one wave.
+template <typename T, int CS, int RPL, int CPW, int SPW, int MODE>
 __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     using Lay = RegLayout<T, RPL, CPW, CS, SPW>;
     constexpr int NMAX = Lay::NMAX, VLEN = Lay::VLEN;
@@ -209,6 +212,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     auto slot_of_grp = [&](int g) { return (g + CPW) % TOT; };
     auto colof = [&](int u) { return (warp + CTA_WARPS * grp(u)) * CS + rank; };
     T a[CPW][RPL];
+    T* const tau_g = p.Twork + (long long)b * p.strideT;   // taus between a MODE 1 and a MODE 2 launch
+#ifdef SLA_LDR_PROFILE
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool prof = (p.prof != nullptr) && (blockIdx.x < CS);
+    long long tq = 0;
+#endif
+    if constexpr (MODE != 2) {
     unsigned active = 0;
     double ssq[TOT];
 #pragma unroll
@@ -422,9 +432,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     select_and_publish(0);
 
 #ifdef SLA_LDR_PROFILE
-    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const bool prof = (p.prof != nullptr) && (blockIdx.x < CS);
-    long long tq = prof ? clock64() : 0;
+    tq = prof ? clock64() : 0;
 #define PROF_MARK(i) do { if (prof) { long long t_ = clock64(); pt[i] += t_ - tq; tq = t_; } } while (0)
 #else
 #define PROF_MARK(i) do { } while (0)
@@ -654,9 +662,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             for (int r = tid; r < n; r += CTA_THREADS) d[r] = dvec[r];
         }
     }
+    if constexpr (MODE == 1) {
+        if (rank == 0)
+            for (int r = tid; r < n; r += CTA_THREADS) tau_g[r] = taus[r];
+    }
     __threadfence();
     cl_barrier<CS>();   // every CTA's reflectors are in global memory and visible; parked columns consumed
     PROF_MARK(5);
+    }   // MODE != 2
+    if constexpr (MODE == 1) return;
+    if constexpr (MODE == 2) {
+        for (int r = tid; r < n; r += CTA_THREADS) taus[r] = tau_g[r];
+        __syncthreads();
+    }
 
     // ------------------------------------------------------------------ Q = H_0 ... H_{n-1} applied to I
     // (column c of Q is touched by the reflectors k <= c only: the shared slots hold the low columns, see colof)
@@ -670,6 +688,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             else sst(u - CPW, t, e);
         }
     }
+    constexpr bool QBLK = (MODE == 2) && !CP && CS == 4 && RPL == 8 && CPW == 4 && SPW == 0;
+    [[maybe_unused]] double* const gq = reinterpret_cast<double*>(smem_raw + Lay::offKeys);          // Gram entries [2][6]
+    [[maybe_unused]] double* const ysc = reinterpret_cast<double*>(smem_raw + Lay::offStageV) + warp * 16;   // per-warp z / y
     {
         T* const ring = vcand;   // [2][QKC][NMAX]
         const int nchunk = (n + QKC_R - 1) / QKC_R;
@@ -697,6 +718,37 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             const T* vb = ring + (size_t)(ch & 1) * QKC_R * NMAX;
             const int k0 = ch * QKC_R;
             const int kcnt = min(QKC_R, n - k0);
+            // Blocked application (Q-only launches of the register shape): four reflectors at a time in compact-WY
+            // form, Q <- Q - V (T (V^T Q)): ONE transposed reduction per four reflectors instead of four.
+            [[maybe_unused]] int nq = 0;
+            if constexpr (QBLK) {
+                nq = kcnt / 4;
+                T* vw = ring + (size_t)(ch & 1) * QKC_R * NMAX;
+                const int rlo = ((k0 >> 5) & ~1) * 32;
+                // (a) masks in place: rows < k -> 0, row k -> 1, rows >= n -> 0 (only rows >= rlo are ever read)
+                for (int e = tid; e < kcnt * (NMAX - rlo); e += CTA_THREADS) {
+                    const int i = e / (NMAX - rlo), r = rlo + e % (NMAX - rlo), k = k0 + i;
+                    if (r < k || r >= n) vw[(size_t)i * NMAX + r] = mk<T>(0.0);
+                    else if (r == k) vw[(size_t)i * NMAX + r] = mk<T>(1.0);
+                }
+                // (b) Gram entries v_i^T v_j (i < j) of every quad, one warp each (masks applied on the fly)
+                if (warp < 6 * nq) {
+                    const int q = warp / 6, pi = warp % 6;
+                    const int jj = (pi < 1) ? 1 : (pi < 3 ? 2 : 3), ii = pi - (jj == 1 ? 0 : (jj == 2 ? 1 : 3));
+                    const int kj = k0 + 4 * q + jj;
+                    const T* vi = vb + (size_t)(4 * q + ii) * NMAX;
+                    const T* vj = vb + (size_t)(4 * q + jj) * NMAX;
+                    double g = 0.0;
+#pragma unroll
+                    for (int t = 0; t < RPL; ++t) {
+                        const int r = lane + 32 * t;
+                        if (r >= kj && r < n) g = fma(real_(vi[r]), (r == kj) ? 1.0 : real_(vj[r]), g);
+                    }
+                    g = warp_sum(g);
+                    if (lane == 0) gq[q * 6 + pi] = g;
+                }
+                __syncthreads();
+            }
             // columns left of the whole chunk are untouched by it
             unsigned qact = 0;
 #pragma unroll
@@ -706,7 +758,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             }
             if (qact) {
                 const int tlo = k0 >> 5;
-                for (int i = kcnt - 1; i >= 0; --i) {
+                for (int i = kcnt - 1; i >= (QBLK ? 4 * nq : 0); --i) {
                     const int k = k0 + i;
                     const T* vk = vb + (size_t)i * NMAX;
                     const T tk = taus[k];
@@ -776,6 +828,79 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                     else SLA_QPASS(0)
 #undef SLA_QPASS
                 }
+                if constexpr (QBLK) {
+                    for (int q = nq - 1; q >= 0; --q) {
+                        const int kq = k0 + 4 * q;
+                        const double* v0p = reinterpret_cast<const double*>(vb) + (size_t)(4 * q) * NMAX + lane;
+                        // columns u < M of this warp lie left of the chunk (c < 64 M <= k0): skipped with their tiles
+#define SLA_QBLOCK(M)                                                                                  \
+    {                                                                                                  \
+        double z[16];                                                                                  \
+        _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) z[i_] = 0.0;                                 \
+        _Pragma("unroll") for (int t = 2 * (M); t < RPL; ++t) {                                        \
+            const double w0 = v0p[32 * t], w1 = v0p[NMAX + 32 * t], w2 = v0p[2 * NMAX + 32 * t],       \
+                         w3 = v0p[3 * NMAX + 32 * t];                                                  \
+            _Pragma("unroll") for (int u = (M); u < 4; ++u) {                                          \
+                z[4 * u + 0] = fma(w0, a[u][t], z[4 * u + 0]);                                         \
+                z[4 * u + 1] = fma(w1, a[u][t], z[4 * u + 1]);                                         \
+                z[4 * u + 2] = fma(w2, a[u][t], z[4 * u + 2]);                                         \
+                z[4 * u + 3] = fma(w3, a[u][t], z[4 * u + 3]);                                         \
+            }                                                                                          \
+        }                                                                                              \
+        const double zz = reduce_transposed<double, 16>(z, lane);   /* lanes 2g, 2g+1: z_g, g = 4u + j */ \
+        if (!(lane & 1)) ysc[lane >> 1] = zz;                                                          \
+        /* T of the quad (forward, column-wise ?larft) from the Gram entries and the taus */           \
+        const double t0 = real_(taus[kq]), t1 = real_(taus[kq + 1]), t2 = real_(taus[kq + 2]),          \
+                     t3 = real_(taus[kq + 3]);                                                         \
+        const double g01 = gq[q * 6 + 0], g02 = gq[q * 6 + 1], g12 = gq[q * 6 + 2], g03 = gq[q * 6 + 3], \
+                     g13 = gq[q * 6 + 4], g23 = gq[q * 6 + 5];                                         \
+        const double T01 = -t1 * (t0 * g01);                                                           \
+        const double T12 = -t2 * (t1 * g12), T02 = -t2 * (t0 * g02 + T01 * g12);                       \
+        const double T23 = -t3 * (t2 * g23), T13 = -t3 * (t1 * g13 + T12 * g23),                       \
+                     T03 = -t3 * (t0 * g03 + T01 * g13 + T02 * g23);                                   \
+        __syncwarp();                                                                                  \
+        {   /* y = T z for the column of this lane's 8-lane group; its first lane publishes it */      \
+            const int ug = lane >> 3;                                                                  \
+            const double2 za = *reinterpret_cast<const double2*>(ysc + 4 * ug);                        \
+            const double2 zb = *reinterpret_cast<const double2*>(ysc + 4 * ug + 2);                    \
+            const double y3 = t3 * zb.y;                                                               \
+            const double y2 = fma(T23, zb.y, t2 * zb.x);                                               \
+            const double y1 = fma(T13, zb.y, fma(T12, zb.x, t1 * za.y));                               \
+            const double y0 = fma(T03, zb.y, fma(T02, zb.x, fma(T01, za.y, t0 * za.x)));               \
+            __syncwarp();                                                                              \
+            if ((lane & 7) == 0) {                                                                     \
+                *reinterpret_cast<double2*>(ysc + 4 * ug) = make_double2(y0, y1);                      \
+                *reinterpret_cast<double2*>(ysc + 4 * ug + 2) = make_double2(y2, y3);                  \
+            }                                                                                          \
+            __syncwarp();                                                                              \
+        }                                                                                              \
+        double y[16];                                                                                  \
+        _Pragma("unroll") for (int u = (M); u < 4; ++u) {                                              \
+            const double2 ya = *reinterpret_cast<const double2*>(ysc + 4 * u);                         \
+            const double2 yb = *reinterpret_cast<const double2*>(ysc + 4 * u + 2);                     \
+            y[4 * u] = ya.x; y[4 * u + 1] = ya.y; y[4 * u + 2] = yb.x; y[4 * u + 3] = yb.y;            \
+        }                                                                                              \
+        __syncwarp();                                                                                  \
+        _Pragma("unroll") for (int t = 2 * (M); t < RPL; ++t) {                                        \
+            const double w0 = v0p[32 * t], w1 = v0p[NMAX + 32 * t], w2 = v0p[2 * NMAX + 32 * t],       \
+                         w3 = v0p[3 * NMAX + 32 * t];                                                  \
+            _Pragma("unroll") for (int u = (M); u < 4; ++u) {                                          \
+                double acc_ = a[u][t];                                                                 \
+                acc_ = fma(-w0, y[4 * u + 0], acc_);                                                   \
+                acc_ = fma(-w1, y[4 * u + 1], acc_);                                                   \
+                acc_ = fma(-w2, y[4 * u + 2], acc_);                                                   \
+                acc_ = fma(-w3, y[4 * u + 3], acc_);                                                   \
+                a[u][t] = acc_;                                                                        \
+            }                                                                                          \
+        }                                                                                              \
+    }
+                        if (tlo >= 6) SLA_QBLOCK(3)
+                        else if (tlo >= 4) SLA_QBLOCK(2)
+                        else if (tlo >= 2) SLA_QBLOCK(1)
+                        else SLA_QBLOCK(0)
+#undef SLA_QBLOCK
+                    }
+                }
             }
             __syncthreads();
         }
@@ -805,8 +930,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
 }
 
 // ---- host side --------------------------------------------------------------------------------------
-template <typename T, int CS, int RPL, int CPW, int SPW = 0> static cudaError_t launch_reg(const LdrArgs<T>& p, cudaStream_t stream) {
-    auto kern = ldr_reg_kernel<T, CS, RPL, CPW, SPW>;
+template <typename T, int CS, int RPL, int CPW, int SPW = 0, int MODE = 0> static cudaError_t launch_reg(const LdrArgs<T>& p, cudaStream_t stream) {
+    auto kern = ldr_reg_kernel<T, CS, RPL, CPW, SPW, MODE>;
     const size_t smem = RegLayout<T, RPL, CPW, CS, SPW>::total;
     if (smem > 227 * 1024) return cudaErrorNotSupported;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -830,7 +955,7 @@ template <typename T, int CS, int RPL, int CPW, int SPW = 0> static cudaError_t 
 
 // how many clusters of this shape the device holds at once (GPC fragmentation included); cached by the callers
 template <typename T, int CS, int RPL, int CPW, int SPW = 0> static int max_clusters_of() {
-    auto kern = ldr_reg_kernel<T, CS, RPL, CPW, SPW>;
+    auto kern = ldr_reg_kernel<T, CS, RPL, CPW, SPW, 0>;
     const size_t smem = RegLayout<T, RPL, CPW, CS, SPW>::total;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     cudaLaunchConfig_t cfg = {};
@@ -881,6 +1006,14 @@ template <> cudaError_t ldr_reg_batched<cplx>(const LdrArgs<cplx>& p, cudaStream
 template <> cudaError_t ldr_hyb_batched<double>(const LdrArgs<double>& p, cudaStream_t s) {
     if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
     if (p.n > 256) return cudaErrorNotSupported;
+    // factorise with the hybrid shape (one wave), then form Q with the register shape, four reflectors per
+    // reduction (compact WY): 1.12 -> 1.08 ms for 64 matrices.  SLA_HYB_SPLITQ=0: everything in the hybrid launch.
+    static const bool splitq = !(getenv("SLA_HYB_SPLITQ") && atoi(getenv("SLA_HYB_SPLITQ")) == 0);
+    if (splitq && p.Twork != nullptr && p.strideT >= p.n) {
+        cudaError_t e = launch_reg<double, 2, 8, 4, 4, 1>(p, s);
+        if (e != cudaSuccess) return e;
+        return launch_reg<double, 4, 8, 4, 0, 2>(p, s);
+    }
     return launch_reg<double, 2, 8, 4, 4>(p, s);
 }
 template <> cudaError_t ldr_hyb_batched<cplx>(const LdrArgs<cplx>&, cudaStream_t) { return cudaErrorNotSupported; }
