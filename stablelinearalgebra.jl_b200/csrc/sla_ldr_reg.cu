@@ -697,15 +697,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         const bool vecq = (((size_t)ldl * sizeof(T)) % 16 == 0) && ((((uintptr_t)Lg) & 15) == 0) && (CP || (n % 2 == 0));
         auto load_chunk = [&](int ch, int buf) {
             T* dstb = ring + (size_t)buf * QKC_R * NMAX;
-            const int per_col = (n + EPV - 1) / EPV;
-            for (int e = tid; e < QKC_R * per_col; e += CTA_THREADS) {
-                const int i = e / per_col, r = (e % per_col) * EPV;
-                const int kk = ch * QKC_R + i;
-                T* dst = dstb + (size_t)i * NMAX + r;
-                if (kk < n && vecq) {
-                    cp_async16(dst, Lg + (long long)kk * ldl + r, 16);
-                } else if (kk < n) {
-                    for (int t = 0; t < EPV; ++t) if (r + t < n) dst[t] = Lg[(long long)kk * ldl + r + t];
+            // 64 threads per reflector, 16-byte pieces (no integer division in the index math)
+            static_assert(CTA_THREADS == 64 * QKC_R, "one 64-thread group per reflector of a chunk");
+            const int i = tid >> 6, kk = ch * QKC_R + i;
+            if (kk < n) {
+                for (int r = (tid & 63) * EPV; r < n; r += 64 * EPV) {
+                    T* dst = dstb + (size_t)i * NMAX + r;
+                    if (vecq) {
+                        cp_async16(dst, Lg + (long long)kk * ldl + r, 16);
+                    } else {
+                        for (int t = 0; t < EPV; ++t) if (r + t < n) dst[t] = Lg[(long long)kk * ldl + r + t];
+                    }
                 }
             }
             cp_async_commit();
@@ -726,10 +728,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
                 T* vw = ring + (size_t)(ch & 1) * QKC_R * NMAX;
                 const int rlo = ((k0 >> 5) & ~1) * 32;
                 // (a) masks in place: rows < k -> 0, row k -> 1, rows >= n -> 0 (only rows >= rlo are ever read)
-                for (int e = tid; e < kcnt * (NMAX - rlo); e += CTA_THREADS) {
-                    const int i = e / (NMAX - rlo), r = rlo + e % (NMAX - rlo), k = k0 + i;
-                    if (r < k || r >= n) vw[(size_t)i * NMAX + r] = mk<T>(0.0);
-                    else if (r == k) vw[(size_t)i * NMAX + r] = mk<T>(1.0);
+                if ((tid >> 6) < kcnt) {
+                    const int i = tid >> 6, k = k0 + i;
+                    for (int r = rlo + (tid & 63); r <= k; r += 64) vw[(size_t)i * NMAX + r] = mk<T>(r == k ? 1.0 : 0.0);
+                    for (int r = n + (tid & 63); r < NMAX; r += 64) vw[(size_t)i * NMAX + r] = mk<T>(0.0);
                 }
                 // (b) Gram entries v_i^T v_j (i < j) of every quad, one warp each (masks applied on the fly)
                 if (warp < 6 * nq) {
