@@ -298,10 +298,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         if constexpr (KPL == 1) {
             km = ckey[lane];
         } else {
-            const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(ckey + lane * KPL);
+            // 16-byte lane stride (conflict-free): keys (2 lane, 2 lane + 1) and, for 128 keys, (64 + 2 lane, 65 + 2 lane)
+            const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(ckey + lane * 2);
             km = q0.x > q0.y ? q0.x : q0.y;
             if constexpr (KPL == 4) {
-                const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(ckey + lane * KPL + 2);
+                const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(ckey + 64 + lane * 2);
                 const unsigned long long k1 = q1.x > q1.y ? q1.x : q1.y;
                 km = k1 > km ? k1 : km;
             }
