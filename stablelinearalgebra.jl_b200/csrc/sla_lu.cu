@@ -33,40 +33,108 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
     for (int r = tid; r < n; r += CTA_THREADS) rowpos[r] = -1;
     for (int p0 = 0; p0 < n; p0 += NB) {
         const int jb = min(NB, n - p0), kend = p0 + jb;
-        // ---- load panel rows [p0, n)
-        for (int i = 0; i < NB; ++i) {
-            for (int r = tid; r < n; r += CTA_THREADS)
-                Ps[(size_t)i * ld + r] = (i < jb && r >= p0) ? A[(long long)(p0 + i) * lda + r] : mk<T>(0.0);
-        }
-        __syncthreads();
-        // ---- unblocked LU of the panel in shared memory
-        for (int j = 0; j < jb; ++j) {
-            const int k = p0 + j;
-            T* colj = Ps + (size_t)j * ld;
-            double bv = -1.0; int bi = 0x7fffffff;
-            for (int r = k + tid; r < n; r += CTA_THREADS) {
-                double v = abs1_(colj[r]);
-                if (v > bv) { bv = v; bi = r; }
-            }
-            int piv = block_argmax(bv, bi, redv, redi);
-            if (piv >= n) piv = k;  // NaN guard
-            if (tid < jb && piv != k) {
-                T* ci = Ps + (size_t)tid * ld;
-                T t = ci[k]; ci[k] = ci[piv]; ci[piv] = t;
-            }
-            if (tid == 0) ipiv[k] = piv;
-            __syncthreads();
-            const T pv = colj[k];
-            if (is_zero(pv)) {
-                if (tid == 0 && info_out && *info_out == 0) *info_out = k + 1;
-            } else {
-                for (int r = k + 1 + tid; r < n; r += CTA_THREADS) {
-                    T l = colj[r] / pv;
-                    colj[r] = l;
-                    for (int i = j + 1; i < jb; ++i) fms(Ps[(size_t)i * ld + r], l, Ps[(size_t)i * ld + k]);
+        if (n <= CTA_THREADS) {
+            // ---- register-row panel LU: thread r holds row r of the panel (NB values) for the whole panel.
+            // Per column: warp argmax -> block maximum (1 barrier), the pivot row and row k change owners through
+            // shared memory (1 barrier), every thread below scales its entry and updates its row from registers.
+            const int r = tid;
+            const bool inrow = (r >= p0 && r < n);
+            T arow[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) arow[i] = (i < jb && inrow) ? A[(long long)(p0 + i) * lda + r] : mk<T>(0.0);
+            T* rowP = Us;            // the pivot row of the current column
+            T* rowK = Us + NB;       // the row it displaces
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                if (j < jb) {
+                    const int k = p0 + j;
+                    double v = (r >= k && r < n) ? abs1_(arow[j]) : -1.0;
+                    int idx = r;
+                    if (!(v >= 0.0)) { v = -1.0; idx = 0x7fffffff; }   // inactive rows and NaNs never win
+                    warp_argmax(v, idx);
+                    if ((tid & 31) == 0) { redv[tid >> 5] = v; redi[tid >> 5] = idx; }
+                    __syncthreads();
+                    double bv = redv[0];
+                    int piv = redi[0];
+#pragma unroll
+                    for (int w = 1; w < CTA_WARPS; ++w) {
+                        const double ov = redv[w];
+                        const int oi = redi[w];
+                        if (ov > bv || (ov == bv && oi < piv)) { bv = ov; piv = oi; }
+                    }
+                    if (piv >= n) piv = k;   // NaN guard
+                    if (r == piv) {
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) rowP[i] = arow[i];
+                    }
+                    if (r == k && piv != k) {
+#pragma unroll
+                        for (int i = 0; i < NB; ++i) rowK[i] = arow[i];
+                    }
+                    if (tid == 0) ipiv[k] = piv;
+                    __syncthreads();
+                    if (piv != k) {
+                        if (r == k) {
+#pragma unroll
+                            for (int i = 0; i < NB; ++i) arow[i] = rowP[i];
+                        } else if (r == piv) {
+#pragma unroll
+                            for (int i = 0; i < NB; ++i) arow[i] = rowK[i];
+                        }
+                    }
+                    const T pv = rowP[j];
+                    if (is_zero(pv)) {
+                        if (tid == 0 && info_out && *info_out == 0) *info_out = k + 1;
+                    } else if (r > k && r < n) {
+                        const T l = arow[j] / pv;
+                        arow[j] = l;
+#pragma unroll
+                        for (int i = j + 1; i < NB; ++i) fms(arow[i], l, rowP[i]);
+                    }
                 }
             }
+            // the factored panel -> shared (the block steps below read it from there)
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                for (int rr = tid; rr < n; rr += CTA_THREADS) Ps[(size_t)i * ld + rr] = (rr >= p0) ? arow[i] : mk<T>(0.0);
+            }
             __syncthreads();
+        } else {
+            // ---- load panel rows [p0, n)
+            for (int i = 0; i < NB; ++i) {
+                for (int r = tid; r < n; r += CTA_THREADS)
+                    Ps[(size_t)i * ld + r] = (i < jb && r >= p0) ? A[(long long)(p0 + i) * lda + r] : mk<T>(0.0);
+            }
+            __syncthreads();
+            // ---- unblocked LU of the panel in shared memory
+            for (int j = 0; j < jb; ++j) {
+                const int k = p0 + j;
+                T* colj = Ps + (size_t)j * ld;
+                double bv = -1.0; int bi = 0x7fffffff;
+                for (int r = k + tid; r < n; r += CTA_THREADS) {
+                    double v = abs1_(colj[r]);
+                    if (v > bv) { bv = v; bi = r; }
+                }
+                int piv = block_argmax(bv, bi, redv, redi);
+                if (piv >= n) piv = k;  // NaN guard
+                if (tid < jb && piv != k) {
+                    T* ci = Ps + (size_t)tid * ld;
+                    T t = ci[k]; ci[k] = ci[piv]; ci[piv] = t;
+                }
+                if (tid == 0) ipiv[k] = piv;
+                __syncthreads();
+                const T pv = colj[k];
+                if (is_zero(pv)) {
+                    if (tid == 0 && info_out && *info_out == 0) *info_out = k + 1;
+                } else {
+                    for (int r = k + 1 + tid; r < n; r += CTA_THREADS) {
+                        T l = colj[r] / pv;
+                        colj[r] = l;
+                        for (int i = j + 1; i < jb; ++i) fms(Ps[(size_t)i * ld + r], l, Ps[(size_t)i * ld + k]);
+                    }
+                }
+                __syncthreads();
+            }
         }
         // ---- panel back to global
         for (int i = 0; i < jb; ++i)
