@@ -173,7 +173,7 @@ def measure_dgemm_peak(torch, seconds=0.6):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE group-product GEMM launch at the C2 shape (N=256, batch 128),
 # from the `ncu --set full` capture summarised in profiles/ncu_gemm_kernel_r1.txt
-NCU_GEMM_TRAFFIC_BYTES_C2 = 98.9e6
+NCU_GEMM_TRAFFIC_BYTES_C2 = 97.5e6
 
 
 def measure_gemm_kernel(torch, sla, cfg, reps=20):
@@ -314,7 +314,7 @@ def run_gpu(args):
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": NCU_GEMM_TRAFFIC_BYTES_C2 if (cfg.N == 256 and cfg.chains == 64 and cfg.dtype.kind != "c") else None,
                 "traffic_unit": "bytes/launch (ncu dram read+write; algorithmic HBM bytes of the launch: 134.7e6)",
-                "dmma_pipe_active_pct_ncu": 78.2,
+                "dmma_pipe_active_pct_ncu": 81.3,
                 "peak_source": "FP64 cuBLAS DGEMM 8192^3 via torch.matmul measured in this run (MEASURED_PEAKS.json "
                                "holds only bf16 and HBM figures; nominal B200 FP64 ~37-40 TFLOP/s)",
                 "launch_ms": gm_ms, "launch_batch": gm_batch, "flops_per_launch": gm_flops,
