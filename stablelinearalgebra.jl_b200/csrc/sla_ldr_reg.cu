@@ -1,19 +1,24 @@
 // Batched LDR factorisation, register-resident version: one thread-block cluster owns one matrix and the
-// matrix lives in the REGISTER FILES of its CTAs for the whole factorisation.
+// matrix lives in the REGISTER FILES (and, in the hybrid shape, half of it in the shared memory) of its CTAs
+// for the whole factorisation.
 //
 // Replaces `ldr!(F, ws)` (src/LDR.jl:160-188: geqp3! + triu/abs/ldiv!/mul_P! + orgqr!) for n <= 256.
-// Same mathematics and same cluster protocol as sla_ldr_cluster.cu (speculative pivot candidates pushed
-// into the peers' shared memory, one cluster barrier per column, no physical column swaps, squared-norm
-// down-dating with LAPACK's cancellation safeguard, TMA store of the reflectors), but:
-//   * a warp owns CPW columns (column-cyclic over CTAs, then over warps) and keeps them as a
-//     CPW x RPL register tile per lane (row r = lane + 32 t): the per-column pass is pure register math --
-//     RPL shared-memory loads for v_k, a dot product per column, a transposed warp reduction, an EAGER
-//     rank-1 update -- with no shared-memory traffic for the matrix at all;
-//   * only the warp that holds the CTA's best column builds the candidate reflector (straight from its
-//     registers) and pushes it to the peers, so the serial FP64 sqrt/div chain is issued once per CTA;
-//   * retired columns (= columns of R') are parked in shared memory and scaled/written at the end;
-//   * Q = H_0...H_{n-1} is formed with the same register tiles: the reflectors stream back through a
-//     cp.async ring and each warp applies them to its columns of the identity, never leaving registers.
+// Same mathematics as LAPACK's ?laqp2/?larfg/?org2r, own formulation:
+//   * a warp owns CPW columns (column-cyclic over CTAs, then over warps) as a CPW x RPL register tile per lane
+//     (row r = lane + 32 t): the per-column pass is register math -- RPL shared-memory loads for v_k, a dot
+//     product per column, a transposed warp reduction, an eager rank-1 update;
+//   * speculative pivots: every CTA picks its best column through packed 64-bit keys (two 32-bit warp `redux`
+//     reductions), the warp that holds it builds the reflector that column WOULD generate and ships it (vector,
+//     then key/beta/tau behind it) with one DSMEM bulk copy per peer that completes on the peer's mbarrier --
+//     the only cluster-wide synchronisation per column; all CTAs then pick the same winner;
+//   * no physical column swaps; squared-norm down-dating with LAPACK's cancellation safeguard, the bookkeeping
+//     replicated in every lane of a column's lane group (no divergence);
+//   * off the critical path (behind the pivot scan): parking of the retired column, the TMA store of the
+//     reflector, the reciprocals of the next down-dating;
+//   * HYBRID shape (SPW > 0): a warp owns SPW more columns in shared memory (thread-private 16-byte pairs), so a
+//     matrix needs half as many SMs and 64 matrices of N = 256 are resident in ONE wave instead of two;
+//   * MODE 0 factorises and forms Q = H_0...H_{n-1} I in one launch (reflectors stream back through a cp.async
+//     ring); MODE 1 only factorises; MODE 2 only forms Q, four reflectors per reduction (compact WY).
 #include <cooperative_groups.h>
 
 #include "sla_cta.cuh"
