@@ -17,6 +17,10 @@ template <typename T, int OPA, int OPB> static cudaError_t gemm_pick_tile(const 
         // waste when the size is a multiple of 80 but not of 64 (N=400).
         static const int force_tile = getenv("SLA_GEMM_TILE") ? atoi(getenv("SLA_GEMM_TILE")) : 0;   // experiments
         if (force_tile == 64) return launch_gemm_cfg<T, OPA, OPB, 64, 64, 32, 32, 16, 3>(p, s);
+        if (force_tile == 6432) return launch_gemm_cfg<T, OPA, OPB, 64, 64, 32, 32, 32, 2>(p, s);
+        if (force_tile == 6424) return launch_gemm_cfg<T, OPA, OPB, 64, 64, 32, 32, 16, 2>(p, s);
+        if (force_tile == 6444) return launch_gemm_cfg<T, OPA, OPB, 64, 64, 32, 32, 16, 4>(p, s);
+        if (force_tile == 6484) return launch_gemm_cfg<T, OPA, OPB, 64, 64, 32, 32, 8, 4>(p, s);
         if (force_tile == 80) return launch_gemm_cfg<T, OPA, OPB, 80, 80, 40, 40, 16, 3>(p, s);
         if (force_tile == 12864) return launch_gemm_cfg<T, OPA, OPB, 128, 64, 64, 32, 16, 3>(p, s);
         if (force_tile == 128) return launch_gemm_cfg<T, OPA, OPB, 128, 128, 64, 32, 16, 3>(p, s);

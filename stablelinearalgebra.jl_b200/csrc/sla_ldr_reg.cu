@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     T* const Rst = reinterpret_cast<T*>(smem_raw + Lay::offRst);           // [16*CPW][NMAX]   (SPW == 0)
     // hybrid: element (su, t) of this lane at scol[(su*RPL/2 + t/2)*64 + (t&1)]  (16-byte pairs of row tiles)
     T* const scol = Rst + ((size_t)(threadIdx.x >> 5) * (SPW > 0 ? SPW : 1) * RPL * 32) + (threadIdx.x & 31) * 2;
+    [[maybe_unused]] const T* const swarp = Rst + ((size_t)(threadIdx.x >> 5) * (SPW > 0 ? SPW : 1) * RPL * 32);
     auto sld = [&](int su, int t) -> T { return scol[(su * (RPL / 2) + (t >> 1)) * 64 + (t & 1)]; };
     auto sst = [&](int su, int t, T v) { scol[(su * (RPL / 2) + (t >> 1)) * 64 + (t & 1)] = v; };
     T* const taus = reinterpret_cast<T*>(smem_raw + Lay::offTau);
@@ -536,12 +537,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             v[t] = (lane + 32 * t < n) ? vcur[lane + 32 * t] : mk<T>(0.0);                             \
         _Pragma("unroll") for (int t = (T0); t < RPL && t < (T0) + 2; ++t)                             \
             if (t == tlo) {                                                                            \
-                _Pragma("unroll") for (int u = 0; u < TOT; ++u) {                                      \
-                    T e_;                                                                              \
-                    if constexpr (SPW > 0) e_ = (u < CPW) ? a[u < CPW ? u : 0][t] : sld(u - CPW, t);   \
-                    else e_ = a[u < CPW ? u : 0][t];                                                   \
-                    e_ = shb(e_, k & 31);                                                              \
+                _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                      \
+                    const T e_ = shb(a[u][t], k & 31);                                                 \
                     if (myu == u) akm = e_;                                                            \
+                }                                                                                      \
+                if constexpr (SPW > 0) {   /* shared slots: straight from the owner lane's cell */      \
+                    if (myu >= CPW) akm = swarp[(k & 31) * 2 + ((myu - CPW) * (RPL / 2) + (t >> 1)) * 64 + (t & 1)]; \
                 }                                                                                      \
             }                                                                                          \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
