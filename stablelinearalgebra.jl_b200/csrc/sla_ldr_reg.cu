@@ -71,7 +71,8 @@ template <typename T, int RPL, int CPW, int CS, int SPW> struct RegLayout {
     static constexpr size_t offBeta = offD + (size_t)NMAX * sizeof(double);        // signed beta_k = R'(k, pivot column k)
     static constexpr size_t offKeys = al16(offBeta + (size_t)NMAX * sizeof(double));   // [2][16*CPW] pivot keys
     static constexpr size_t offPos = offKeys + 2 * (size_t)CTA_WARPS * (CPW + SPW) * sizeof(unsigned long long);   // pivot position per local column
-    static constexpr size_t total = offPos + (size_t)CTA_WARPS * (CPW + SPW) * sizeof(int) + 64;
+    static constexpr size_t offWsc = al16(offPos + (size_t)CTA_WARPS * (CPW + SPW) * sizeof(int));   // per-warp w broadcast (hybrid)
+    static constexpr size_t total = offWsc + (size_t)CTA_WARPS * 8 * sizeof(double) + 64;
 };
 
 template <int CS> __device__ __forceinline__ void cl_barrier() {
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     // hybrid: element (su, t) of this lane at scol[(su*RPL/2 + t/2)*64 + (t&1)]  (16-byte pairs of row tiles)
     T* const scol = Rst + ((size_t)(threadIdx.x >> 5) * (SPW > 0 ? SPW : 1) * RPL * 32) + (threadIdx.x & 31) * 2;
     [[maybe_unused]] const T* const swarp = Rst + ((size_t)(threadIdx.x >> 5) * (SPW > 0 ? SPW : 1) * RPL * 32);
+    [[maybe_unused]] double* const wsc = reinterpret_cast<double*>(smem_raw + Lay::offWsc) + (threadIdx.x >> 5) * 8;
     auto sld = [&](int su, int t) -> T { return scol[(su * (RPL / 2) + (t >> 1)) * 64 + (t & 1)]; };
     auto sst = [&](int su, int t, T v) { scol[(su * (RPL / 2) + (t >> 1)) * 64 + (t & 1)] = v; };
     T* const taus = reinterpret_cast<T*>(smem_raw + Lay::offTau);
@@ -573,8 +575,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         TR(k, 2);                                                                                      \
         myw = conj_(tauk) * reduce_transposed<T, TOT>(dot, lane);                                      \
         TR(k, 3);                                                                                      \
+        [[maybe_unused]] double wv_[8];                                                                \
+        if constexpr (SPW > 0) {   /* w of the 8 columns through a per-warp scratch: 1 store + 4 loads, not 16 shuffles */ \
+            if ((lane % FLS) == 0) wsc[lane / FLS] = real_(myw);                                       \
+            __syncwarp();                                                                              \
+            _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                         \
+                const double2 w2_ = *reinterpret_cast<const double2*>(wsc + 2 * i_);                   \
+                wv_[2 * i_] = w2_.x; wv_[2 * i_ + 1] = w2_.y;                                          \
+            }                                                                                          \
+            __syncwarp();                                                                              \
+        }                                                                                              \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
-            const T wu = shb(myw, u * FLS);                                                            \
+            T wu;                                                                                      \
+            if constexpr (SPW > 0) wu = mk<T>(wv_[u]); else wu = shb(myw, u * FLS);                    \
             if ((active >> u) & 1u) {                                                                  \
                 SLA_KEEP_BRANCH;                                                                       \
                 _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], wu);             \
@@ -582,7 +595,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         }                                                                                              \
         if constexpr (SPW > 0) {                                                                       \
             _Pragma("unroll") for (int su = 0; su < SPW; ++su) {                                       \
-                const double wu = real_(shb(myw, (CPW + su) * FLS));                                   \
+                const double wu = wv_[CPW + su];                                                       \
                 if ((active >> (CPW + su)) & 1u) {                                                     \
                     SLA_KEEP_BRANCH;                                                                   \
                     _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                            \
@@ -808,8 +821,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         }                                                                                              \
         const T mydot = reduce_transposed<T, TOT>(dot, lane);                                          \
         const T myw = tk * mydot;                                                                      \
+        [[maybe_unused]] double wv_[8];                                                                \
+        if constexpr (SPW > 0) {   /* w of the 8 columns through a per-warp scratch: 1 store + 4 loads, not 16 shuffles */ \
+            if ((lane % FLS) == 0) wsc[lane / FLS] = real_(myw);                                       \
+            __syncwarp();                                                                              \
+            _Pragma("unroll") for (int i_ = 0; i_ < 4; ++i_) {                                         \
+                const double2 w2_ = *reinterpret_cast<const double2*>(wsc + 2 * i_);                   \
+                wv_[2 * i_] = w2_.x; wv_[2 * i_ + 1] = w2_.y;                                          \
+            }                                                                                          \
+            __syncwarp();                                                                              \
+        }                                                                                              \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
-            const T wu = shb(myw, u * FLS);                                                            \
+            T wu;                                                                                      \
+            if constexpr (SPW > 0) wu = mk<T>(wv_[u]); else wu = shb(myw, u * FLS);                    \
             if ((qact >> u) & 1u) {                                                                    \
                 SLA_KEEP_BRANCH;                                                                       \
                 _Pragma("unroll") for (int t = (T0); t < RPL; ++t) fms(a[u][t], v[t], wu);             \
@@ -817,7 +841,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
         }                                                                                              \
         if constexpr (SPW > 0) {                                                                       \
             _Pragma("unroll") for (int su = 0; su < SPW; ++su) {                                       \
-                const double wu = real_(shb(myw, (CPW + su) * FLS));                                   \
+                const double wu = wv_[CPW + su];                                                       \
                 if ((qact >> (CPW + su)) & 1u) {                                                       \
                     SLA_KEEP_BRANCH;                                                                   \
                     _Pragma("unroll") for (int t = (T0); t < RPL; t += 2) {                            \
