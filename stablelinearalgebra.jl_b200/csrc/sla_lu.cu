@@ -8,6 +8,8 @@
 // U12 comes from a register-resident forward substitution and the rank-NB trailing update runs on
 // DMMA from the shared panels.  The inverse is formed as X = U^-1 (L^-1 P) by two blocked triangular
 // sweeps built from the same pieces (mathematically the same inverse ?getri returns).
+#include <cstdio>
+
 #include "sla_cta.cuh"
 #include "sla_kernels.h"
 
@@ -26,13 +28,25 @@ template <typename T> __host__ __device__ inline size_t lu_smem_bytes(int n, int
     return b + 64;
 }
 
+#ifdef SLA_LU_PROFILE
+#define LUP_DECL long long lup_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long lupt_ = clock64();
+#define LUP(i) do { __syncthreads(); long long t_ = clock64(); lup_[i] += t_ - lupt_; lupt_ = t_; } while (0)
+#define LUP_DUMP(tag) do { if (blockIdx.x == 0 && threadIdx.x == 0) printf("%s: panelLU %lld  store %lld  permsim %lld  permapply %lld  U12 %lld  update %lld  other %lld\n", tag, lup_[0], lup_[1], lup_[2], lup_[3], lup_[4], lup_[5], lup_[6]); } while (0)
+#else
+#define LUP_DECL
+#define LUP(i) do { } while (0)
+#define LUP_DUMP(tag) do { } while (0)
+#endif
+
 template <typename T, int NB>
 __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int ld, int* ipiv, int* rowpos,
                           int* tl, int* tsrc, double* redv, int* redi, int* misc, int* info_out) {
     const int tid = threadIdx.x;
     for (int r = tid; r < n; r += CTA_THREADS) rowpos[r] = -1;
+    LUP_DECL
     for (int p0 = 0; p0 < n; p0 += NB) {
         const int jb = min(NB, n - p0), kend = p0 + jb;
+        LUP(6);
         if (n <= CTA_THREADS) {
             // ---- register-row panel LU: thread r holds row r of the panel (NB values) for the whole panel.
             // Per column: warp argmax -> block maximum (1 barrier), the pivot row and row k change owners through
@@ -136,9 +150,11 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
                 __syncthreads();
             }
         }
+        LUP(0);
         // ---- panel back to global
         for (int i = 0; i < jb; ++i)
             for (int r = p0 + tid; r < n; r += CTA_THREADS) A[(long long)(p0 + i) * lda + r] = Ps[(size_t)i * ld + r];
+        LUP(1);
         // ---- net row permutation of this panel (thread 0 simulates the jb interchanges)
         if (tid == 0) {
             int nt = jb;
@@ -154,6 +170,7 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
             misc[0] = nt;
         }
         __syncthreads();
+        LUP(2);
         {
             const int nt = misc[0];
             const int ncols_out = n - jb;             // columns outside the panel: [0,p0) U [kend,n)
@@ -175,6 +192,7 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
                 __syncthreads();
             }
         }
+        LUP(3);
         if (kend < n) {
             // ---- U12 = L11^-1 A12  (thread per column, registers)
             for (int c = kend + tid; c < n; c += CTA_THREADS) {
@@ -196,10 +214,13 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
                 }
             }
             __syncthreads();
+            LUP(4);
             cta_rank_update<T, false>(A, lda, kend, n, kend, n, Ps, Us, ld, jb, n - 1);
             __syncthreads();
+            LUP(5);
         }
     }
+    LUP_DUMP("lu_factor");
 }
 
 // logdet = sum log|u_ii|, sgn = prod sign(u_ii) * (-1)^{#interchanges}   (src/lu.jl:128-139)
