@@ -159,6 +159,9 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (sizeof(T) == 8 &&
 
     const int KT = (p.K + BK - 1) / BK;
     auto load_stage = [&](int stage, int kt) {
+#ifdef SLA_GEMM_ABLATE_LOADS   // timing experiment only (wrong results): no global->shared traffic after the prologue
+        if (kt >= STAGES - 1) return;
+#endif
         T* sa = smem + stage * STAGE_ELEMS;
         T* sb = sa + TileA::ELEMS;
         TileA::template load<NT, VEC>(sa, A, p.lda, m0, kt * BK, p.M, p.K, tid);
