@@ -62,19 +62,45 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
             for (int j = 0; j < NB; ++j) {
                 if (j < jb) {
                     const int k = p0 + j;
-                    double v = (r >= k && r < n) ? abs1_(arow[j]) : -1.0;
-                    int idx = r;
-                    if (!(v >= 0.0)) { v = -1.0; idx = 0x7fffffff; }   // inactive rows and NaNs never win
-                    warp_argmax(v, idx);
-                    if ((tid & 31) == 0) { redv[tid >> 5] = v; redi[tid >> 5] = idx; }
-                    __syncthreads();
-                    double bv = redv[0];
-                    int piv = redi[0];
+                    int piv;
+                    if constexpr (!is_cplx<T>::value) {
+                        // exact 64-bit maximum of |a| by two 32-bit warp reductions (the bit pattern of a non-negative
+                        // double is monotone), first maximal row by a ballot; 0 = inactive row or NaN
+                        const double v = (r >= k && r < n) ? abs1_(arow[j]) : -1.0;
+                        const unsigned long long key = (v >= 0.0) ? (unsigned long long)__double_as_longlong(v) + 1ull : 0ull;
+                        const unsigned khi = (unsigned)(key >> 32);
+                        const unsigned mhi = __reduce_max_sync(0xffffffffu, khi);
+                        const unsigned mlo = __reduce_max_sync(0xffffffffu, khi == mhi ? (unsigned)key : 0u);
+                        const unsigned long long wk = ((unsigned long long)mhi << 32) | mlo;
+                        const unsigned who = __ballot_sync(0xffffffffu, key == wk);
+                        if ((tid & 31) == 0) {
+                            reinterpret_cast<unsigned long long*>(redv)[tid >> 5] = wk;
+                            redi[tid >> 5] = (wk != 0ull) ? (tid & ~31) + __ffs(who) - 1 : 0x7fffffff;
+                        }
+                        __syncthreads();
+                        const int l16 = tid & 15;
+                        const unsigned long long ok = reinterpret_cast<const unsigned long long*>(redv)[l16];
+                        const unsigned ohi = (unsigned)(ok >> 32);
+                        const unsigned ghi = __reduce_max_sync(0xffffffffu, ohi);
+                        const unsigned glo = __reduce_max_sync(0xffffffffu, ohi == ghi ? (unsigned)ok : 0u);
+                        const unsigned long long gk = ((unsigned long long)ghi << 32) | glo;
+                        const unsigned gwho = __ballot_sync(0xffffffffu, ok == gk) & 0xffffu;   // warps in row order
+                        piv = (gk != 0ull) ? redi[__ffs(gwho) - 1] : 0x7fffffff;
+                    } else {
+                        double v = (r >= k && r < n) ? abs1_(arow[j]) : -1.0;
+                        int idx = r;
+                        if (!(v >= 0.0)) { v = -1.0; idx = 0x7fffffff; }   // inactive rows and NaNs never win
+                        warp_argmax(v, idx);
+                        if ((tid & 31) == 0) { redv[tid >> 5] = v; redi[tid >> 5] = idx; }
+                        __syncthreads();
+                        double bv = redv[0];
+                        piv = redi[0];
 #pragma unroll
-                    for (int w = 1; w < CTA_WARPS; ++w) {
-                        const double ov = redv[w];
-                        const int oi = redi[w];
-                        if (ov > bv || (ov == bv && oi < piv)) { bv = ov; piv = oi; }
+                        for (int w = 1; w < CTA_WARPS; ++w) {
+                            const double ov = redv[w];
+                            const int oi = redi[w];
+                            if (ov > bv || (ov == bv && oi < piv)) { bv = ov; piv = oi; }
+                        }
                     }
                     if (piv >= n) piv = k;   // NaN guard
                     if (r == piv) {
@@ -100,7 +126,13 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
                     if (is_zero(pv)) {
                         if (tid == 0 && info_out && *info_out == 0) *info_out = k + 1;
                     } else if (r > k && r < n) {
-                        const T l = arow[j] / pv;
+                        T l;
+                        if constexpr (!is_cplx<T>::value) {   // reciprocal scaling like ?getf2 (division below sfmin)
+                            if (fabs(pv) >= 2.2250738585072014e-308) l = arow[j] * __drcp_rn(pv);
+                            else l = arow[j] / pv;
+                        } else {
+                            l = arow[j] / pv;
+                        }
                         arow[j] = l;
 #pragma unroll
                         for (int i = j + 1; i < NB; ++i) fms(arow[i], l, rowP[i]);
