@@ -209,17 +209,23 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
             const int ch = (NB * ld) / (2 * NB);      // columns per chunk staged through Us ([q][cl], q < 2*NB)
             for (int cb = 0; cb < ncols_out; cb += ch) {
                 const int cn = min(ch, ncols_out - cb);
-                for (int e = tid; e < cn * nt; e += CTA_THREADS) {
-                    int q = e / cn, cl = e % cn;
-                    int c = cb + cl; c = (c < p0) ? c : c + jb;
-                    Us[(size_t)q * ch + cl] = A[(long long)c * lda + tsrc[q]];
+                // a warp per touched row, lanes over the columns (no integer division in the index math)
+                for (int q = tid >> 5; q < nt; q += CTA_WARPS) {
+                    const int rs_ = tsrc[q];
+                    if (rs_ == tl[q]) continue;   // this row stays where it is
+                    for (int cl = tid & 31; cl < cn; cl += 32) {
+                        int c = cb + cl; c = (c < p0) ? c : c + jb;
+                        Us[(size_t)q * ch + cl] = A[(long long)c * lda + rs_];
+                    }
                 }
                 __syncthreads();
-                for (int e = tid; e < cn * nt; e += CTA_THREADS) {
-                    int q = e / cn, cl = e % cn;
-                    if (tsrc[q] == tl[q]) continue;
-                    int c = cb + cl; c = (c < p0) ? c : c + jb;
-                    A[(long long)c * lda + tl[q]] = Us[(size_t)q * ch + cl];
+                for (int q = tid >> 5; q < nt; q += CTA_WARPS) {
+                    const int rd_ = tl[q];
+                    if (tsrc[q] == rd_) continue;
+                    for (int cl = tid & 31; cl < cn; cl += 32) {
+                        int c = cb + cl; c = (c < p0) ? c : c + jb;
+                        A[(long long)c * lda + rd_] = Us[(size_t)q * ch + cl];
+                    }
                 }
                 __syncthreads();
             }
