@@ -292,7 +292,7 @@ __device__ void lu_logdet(const T* __restrict__ A, int lda, int n, const int* ip
 // X = A^-1 * RHS from the LU factors (RHS = identity when rhs == nullptr, i.e. the inverse).
 template <typename T, int NB>
 __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restrict__ X, int ldx, T* Ps, T* Us,
-                           int ld, const int* ipiv, int* rowpos, const T* __restrict__ rhs, int ldrhs) {
+                           int ld, const int* ipiv, int* rowpos, const T* __restrict__ rhs, int ldrhs, T* rdiag) {
     const int tid = threadIdx.x;
     // X = P (row-permuted identity): row r of P*I is e_{src(r)}
     for (int r = tid; r < n; r += CTA_THREADS) rowpos[r] = r;
@@ -344,6 +344,9 @@ __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restric
             for (int r = tid; r < n; r += CTA_THREADS)
                 Ps[(size_t)i * ld + r] = (i < jb && r <= p0 + i) ? A[(long long)(p0 + i) * lda + r] : mk<T>(0.0);
         __syncthreads();
+        // reciprocals of the panel's diagonal, once per panel (the substitution below multiplies)
+        if (tid < jb) rdiag[tid] = mk<T>(1.0) / Ps[(size_t)tid * ld + p0 + tid];
+        __syncthreads();
         for (int c = tid; c < n; c += CTA_THREADS) {
             T a[NB];
             T* col = X + (long long)c * ldx + p0;
@@ -355,7 +358,7 @@ __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restric
 #pragma unroll
                     for (int q = i + 1; q < NB; ++q)
                         if (q < jb) fms(a[i], Ps[(size_t)q * ld + p0 + i], a[q]);
-                    a[i] = a[i] / Ps[(size_t)i * ld + p0 + i];
+                    a[i] = a[i] * rdiag[i];
                 }
             }
 #pragma unroll
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) lu_kernel(LuArgs<T> p) {
     if (p.invert) {
         T* X = p.X + (long long)b * p.strideX;
         T* rhs = p.rhs ? p.rhs + (long long)b * p.strideRhs : nullptr;
-        lu_inverse<T, NB>(A, p.lda, n, X, p.ldx, Ps, Us, ld, ipiv, rowpos, rhs, p.ldrhs);
+        lu_inverse<T, NB>(A, p.lda, n, X, p.ldx, Ps, Us, ld, ipiv, rowpos, rhs, p.ldrhs, redt);
         if (rhs) {   // ldiv_lu!: the solution replaces the right-hand side (src/lu.jl:167-176)
             __syncthreads();
             for (int c = tid >> 5; c < n; c += CTA_WARPS)
