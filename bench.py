@@ -12,6 +12,8 @@ region.  Multi-GPU: the batch of chains is sharded, each rank runs `chains` chai
 scaling) and a single small NCCL all-reduce per step combines the cross-walker sums of log|det| and
 sign.  `--impl reference` times the CPU restatement of the reference (oracle/, C over ILP64 OpenBLAS
 LAPACK; Julia is not installable here) on all host cores, one chain per thread, 1 BLAS thread each.
+The oracle is executed in exactly two places: that reference arm and the `cpu_baseline` leg (rank 0, one GPU); the
+`parity` key compares the GPU results of chains 0..1 with the results the cpu_baseline leg computed for the same chains.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -59,25 +61,30 @@ def config_json(cfg, n_gpus, extra=None):
 # ----------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle's C restatement on the host cores
 # ----------------------------------------------------------------------------------------------------
-def cpu_run(cfg, chains, threads):
+def cpu_run(cfg, chains, threads, keep=0):
+    """Time the CPU arm on chains 0..chains-1; with `keep` also return (G, logdet, sign) of the first `keep` chains."""
     from oracle import c_oracle
     expK = cfg.expK()
     fields = cfg.fields(range(chains))
     t0 = time.perf_counter()
-    c_oracle.eval_batch(expK, fields, cfg.lam, cfg.n_stab, cfg.inverse, nthreads=threads)
-    return time.perf_counter() - t0
+    G, ld, sg = c_oracle.eval_batch(expK, fields, cfg.lam, cfg.n_stab, cfg.inverse, nthreads=threads)
+    t = time.perf_counter() - t0
+    return (t, (G[:keep], ld[:keep], sg[:keep])) if keep else t
 
 
-def cpu_baseline(cfg, budget_s=12.0):
+def cpu_baseline(cfg, budget_s=12.0, keep=2):
+    """The cpu_baseline leg.  Its first pass evaluates chains 0..cores-1 -- the ids rank 0 evaluates on the GPU -- so the
+    results of the first `keep` chains double as the parity check of the line (no second run of the oracle)."""
     from oracle import c_oracle
     cores = os.cpu_count() or 1
-    t1 = cpu_run(cfg, cores, cores)                      # one chain per core
+    keep = min(keep, cores)
+    t1, ref = cpu_run(cfg, cores, cores, keep=keep)      # one chain per core
     rounds = max(1, min(8, int(budget_s / max(t1, 1e-3))))
     chains = cores * rounds
     t = cpu_run(cfg, chains, cores) if rounds > 1 else t1
     return {"value": chains / t, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{chains} chains of the same workload ({cfg.name} size), {cores} worker threads x 1 BLAS "
-                      f"thread, {t:.2f} s wall; C restatement of the reference over {c_oracle.blas_config()}"}
+                      f"thread, {t:.2f} s wall; C restatement of the reference over {c_oracle.blas_config()}"}, ref
 
 
 def run_reference(args):
@@ -293,17 +300,7 @@ def run_gpu(args):
     h2d = expK_h.numel() * expK_h.element_size() + fields_h.numel()
     d2h = sum(t.numel() * t.element_size() for t in (G_h, logdet_h, sign_h))
 
-    # parity spot check of what was just computed (norm-wise, vs the CPU oracle) -- outside the timed region
-    parity = None
-    if rank == 0 and not args.no_parity:
-        from oracle import c_oracle
-        k = min(2, chains)
-        Gr, lr, sr = c_oracle.eval_batch(cfg.expK(), cfg.fields(list(chain_ids)[:k]), cfg.lam, cfg.n_stab, cfg.inverse, k)
-        Gg = sla.to_host(G[:k])
-        parity = {"chains_checked": k,
-                  "max_rel_err_G": float(max(np.max(np.abs(Gg[i] - Gr[i])) / np.max(np.abs(Gr[i])) for i in range(k))),
-                  "max_abs_err_logdet": float(np.max(np.abs(logdet_h.numpy()[:k] - lr))),
-                  "sign_mismatch": int(np.sum(np.abs(sign_h.numpy()[:k] - sr) > 1e-9))}
+    parity = None   # filled from the cpu_baseline leg below (rank 0, one GPU): same chain ids on both sides
 
     roof = cpub = None
     if rank == 0:
@@ -321,7 +318,14 @@ def run_gpu(args):
                 "step_tflops": cfg.flops_per_eval() * chains / (ms_total / args.steps * 1e-3) / 1e12,
                 "step_frac_of_peak": cfg.flops_per_eval() * chains / (ms_total / args.steps * 1e-3) / 1e12 / peak}
         if world == 1 and not args.no_cpu:
-            cpub = cpu_baseline(cfg)
+            cpub, (Gr, lr, sr) = cpu_baseline(cfg)
+            k = min(len(lr), chains)
+            if k > 0 and not args.no_parity:   # chains 0..k-1 of this rank against the same chains of the CPU leg
+                Gg = sla.to_host(G[:k])
+                parity = {"chains_checked": k,
+                          "max_rel_err_G": float(max(np.max(np.abs(Gg[i] - Gr[i])) / np.max(np.abs(Gr[i])) for i in range(k))),
+                          "max_abs_err_logdet": float(np.max(np.abs(logdet_h.numpy()[:k] - lr[:k]))),
+                          "sign_mismatch": int(np.sum(np.abs(sign_h.numpy()[:k] - sr[:k]) > 1e-9))}
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
