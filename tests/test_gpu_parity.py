@@ -531,6 +531,25 @@ def test_ldr_hybrid_shape(S, n):
     check_ldr(S, A)
 
 
+def test_ldr_hybrid_shape_edge_inputs(S):
+    """Hybrid shape on inputs the reference's tests care about: identity (trivial reflectors, pivot ties), a column scale
+    spread of 300 decades sorted the way a DQMC chain hands it over, and dependent columns (exact cancellation)."""
+    n, batch = 200, 36
+    check_ldr(S, np.repeat(np.eye(n)[None], batch, axis=0))
+    rng = np.random.default_rng(77)
+    A = rng.standard_normal((batch, n, n)) * (10.0 ** np.linspace(150, -150, n))[None, None, :]
+    check_ldr(S, A)
+    B = rng.standard_normal((batch, n, n))
+    B[:, :, 150] = B[:, :, 3]          # exactly dependent columns: one d ~ 0 (R may then hold non-finite entries, as in LAPACK)
+    dB = S.to_device(B)
+    F = S.ldr(dB, S.ldr_workspace(dB))
+    L, d, R = S.to_host(F.L), F.d.cpu().numpy(), S.to_host(F.R)
+    for b in range(batch):
+        assert np.max(np.abs(L[b].T @ L[b] - np.eye(n))) < 1e-13 * n
+        if np.isfinite(R[b]).all():
+            assert relerr((L[b] * d[b][None, :]) @ R[b], B[b]) < 1e-12
+
+
 @pytest.mark.parametrize("algo", ["streaming", "cluster", "hyb", "hyb+oneq"])
 def test_other_ldr_kernels_subprocess(algo):
     """Default LDR kernel for n <= 256 is the register-resident cluster kernel.  The shared-memory cluster
