@@ -29,6 +29,8 @@ template <typename T> int ldr_reg_cluster_size(int n);
 template <typename T> cudaError_t ldr_hyb_batched(const LdrArgs<T>& p, cudaStream_t s);
 template <typename T> int ldr_hyb_cluster_size(int n);
 void ldr_n256_resident(int* reg_clusters, int* hyb_clusters);
+// Q = H_0...H_{n-1} I on the FP64 tensor cores after a factorisation-only launch (real, n <= 256; taus in p.Twork)
+cudaError_t orgq_dmma_batched(const LdrArgs<double>& p, cudaStream_t s);
 
 // ---- LU / inverse with log|det| and sign (sla_lu.cu) ----------------------------------------
 template <typename T> struct LuArgs {

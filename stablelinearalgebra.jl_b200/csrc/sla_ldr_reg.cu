@@ -1045,6 +1045,9 @@ template <> cudaError_t ldr_hyb_batched<double>(const LdrArgs<double>& p, cudaSt
     if (splitq && p.Twork != nullptr && p.strideT >= p.n) {
         cudaError_t e = launch_reg<double, 2, 8, 4, 4, 1>(p, s);
         if (e != cudaSuccess) return e;
+        // SLA_Q_DMMA=1: Q on the tensor cores (sla_orgq.cu; correct, but 0.325 vs 0.275 ms -- off by default)
+        static const bool qdmma = getenv("SLA_Q_DMMA") && atoi(getenv("SLA_Q_DMMA")) != 0;
+        if (qdmma) return orgq_dmma_batched(p, s);
         return launch_reg<double, 4, 8, 4, 0, 2>(p, s);
     }
     return launch_reg<double, 2, 8, 4, 4>(p, s);
