@@ -72,7 +72,7 @@ template <typename T, int RPL, int CPW, int CS, int SPW> struct RegLayout {
     static constexpr size_t offKeys = al16(offBeta + (size_t)NMAX * sizeof(double));   // [2][16*CPW] pivot keys
     static constexpr size_t offPos = offKeys + 2 * (size_t)CTA_WARPS * (CPW + SPW) * sizeof(unsigned long long);   // pivot position per local column
     static constexpr size_t offWsc = al16(offPos + (size_t)CTA_WARPS * (CPW + SPW) * sizeof(int));   // per-warp w broadcast (hybrid)
-    static constexpr size_t total = offWsc + (size_t)CTA_WARPS * 8 * sizeof(double) + 64;
+    static constexpr size_t total = offWsc + (size_t)CTA_WARPS * 16 * sizeof(double) + 64;   // [warp][8 w | 4 row-k elements | 4 spare]
 };
 
 template <int CS> __device__ __forceinline__ void cl_barrier() {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     // hybrid: element (su, t) of this lane at scol[(su*RPL/2 + t/2)*64 + (t&1)]  (16-byte pairs of row tiles)
     T* const scol = Rst + ((size_t)(threadIdx.x >> 5) * (SPW > 0 ? SPW : 1) * RPL * 32) + (threadIdx.x & 31) * 2;
     [[maybe_unused]] const T* const swarp = Rst + ((size_t)(threadIdx.x >> 5) * (SPW > 0 ? SPW : 1) * RPL * 32);
-    [[maybe_unused]] double* const wsc = reinterpret_cast<double*>(smem_raw + Lay::offWsc) + (threadIdx.x >> 5) * 8;
+    [[maybe_unused]] double* const wsc = reinterpret_cast<double*>(smem_raw + Lay::offWsc) + (threadIdx.x >> 5) * 16;
     auto sld = [&](int su, int t) -> T { return scol[(su * (RPL / 2) + (t >> 1)) * 64 + (t & 1)]; };
     auto sst = [&](int su, int t, T v) { scol[(su * (RPL / 2) + (t >> 1)) * 64 + (t & 1)] = v; };
     T* const taus = reinterpret_cast<T*>(smem_raw + Lay::offTau);
@@ -539,12 +539,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             v[t] = (lane + 32 * t < n) ? vcur[lane + 32 * t] : mk<T>(0.0);                             \
         _Pragma("unroll") for (int t = (T0); t < RPL && t < (T0) + 2; ++t)                             \
             if (t == tlo) {                                                                            \
-                _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                      \
-                    const T e_ = shb(a[u][t], k & 31);                                                 \
-                    if (myu == u) akm = e_;                                                            \
-                }                                                                                      \
-                if constexpr (SPW > 0) {   /* shared slots: straight from the owner lane's cell */      \
-                    if (myu >= CPW) akm = swarp[(k & 31) * 2 + ((myu - CPW) * (RPL / 2) + (t >> 1)) * 64 + (t & 1)]; \
+                if constexpr (SPW > 0 && CPW == 4) {                                                   \
+                    /* register slots: the owner lane of row k drops its 4 values into the warp's scratch (2 stores +  \
+                       1 load instead of 8 shuffles); shared slots: straight from the owner lane's cell */               \
+                    if (lane == (k & 31)) {                                                            \
+                        *reinterpret_cast<double2*>(wsc + 8) = make_double2(real_(a[0][t]), real_(a[1][t]));  \
+                        *reinterpret_cast<double2*>(wsc + 10) = make_double2(real_(a[2][t]), real_(a[3][t])); \
+                    }                                                                                  \
+                    __syncwarp();                                                                      \
+                    if (myu < CPW) akm = mk<T>(wsc[8 + myu]);                                          \
+                    else akm = swarp[(k & 31) * 2 + ((myu - CPW) * (RPL / 2) + (t >> 1)) * 64 + (t & 1)]; \
+                } else {                                                                               \
+                    _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                  \
+                        const T e_ = shb(a[u][t], k & 31);                                             \
+                        if (myu == u) akm = e_;                                                        \
+                    }                                                                                  \
                 }                                                                                      \
             }                                                                                          \
         _Pragma("unroll") for (int u = 0; u < CPW; ++u) {                                              \
