@@ -1054,8 +1054,9 @@ template <> cudaError_t ldr_hyb_batched<double>(const LdrArgs<double>& p, cudaSt
     if (splitq && p.Twork != nullptr && p.strideT >= p.n) {
         cudaError_t e = launch_reg<double, 2, 8, 4, 4, 1>(p, s);
         if (e != cudaSuccess) return e;
-        // SLA_Q_DMMA=1: Q on the tensor cores (sla_orgq.cu; correct, but 0.325 vs 0.275 ms -- off by default)
-        static const bool qdmma = getenv("SLA_Q_DMMA") && atoi(getenv("SLA_Q_DMMA")) != 0;
+        // Q on the FP64 tensor cores (sla_orgq.cu: 0.215 ms for 64 matrices); SLA_Q_DMMA=0: the vector-unit MODE 2
+        // launch of this kernel (0.275 ms)
+        static const bool qdmma = !(getenv("SLA_Q_DMMA") && atoi(getenv("SLA_Q_DMMA")) == 0);
         if (qdmma) return orgq_dmma_batched(p, s);
         return launch_reg<double, 4, 8, 4, 0, 2>(p, s);
     }

@@ -5,8 +5,8 @@
 // Q formation has no pivoting, so the reflectors are applied eight at a time in compact-WY form,
 //     Q <- Q - V (T (V^T Q)),
 // and every product is a DMMA.8x8x4 chain whose operands are ALREADY where the tensor core wants them:
-//   * a warp owns 8 columns of Q (all 256 rows) as accumulator fragments: lane (fi = lane/4, fk = lane%4) holds
-//     rows 8s + 2fk + {0,1} of column fi of its group, s = 0..31 -- 64 doubles per lane, never moved;
+//   * Q lives in accumulator fragments: lane (fi = lane/4, fk = lane%4) of warp w holds rows 8s + 2fk + {0,1}, s = w + 8i,
+//     of column 32g + 4fi + (CTA rank) for the 8 column groups g -- 64 doubles per lane, never moved;
 //   * Z^T = Q^T V  : A operand = the lane's own Q value (the k-slot <-> row assignment is free, so it is chosen
 //     to be the row the lane holds), B operand = V from shared memory (one 16-byte load per two steps);
 //   * Y^T = Z^T T^T: two DMMAs, A = the Z^T fragment as it came out, B = T from shared memory;
@@ -16,11 +16,10 @@
 // A cluster of 4 CTAs forms the Q of one matrix (column c -> CTA c % 4); the only cluster-wide step is the barrier
 // before Q overwrites the reflectors in L.
 //
-// STATUS (round 1): correct (orthogonality 2e-15, all sizes), but NOT faster than the vector-unit MODE 2 launch of
-// sla_ldr_reg.cu: 0.325 ms vs 0.275 ms for 64 matrices of N = 256 -- every warp re-reads the whole chunk of V from shared
-// memory in both sweeps (8x redundant traffic, DMMA pipe 18 % busy), and the per-chunk barriers leave the light column
-// groups waiting for the heavy one.  It is therefore OFF by default (SLA_Q_DMMA=1 selects it); a next version has to
-// give a warp more columns per V fragment (two warps per row half with a shared-memory reduction of Z).
+// Round-1 history: a column-distributed version (a warp owns 8 columns, all rows) was correct but slower than the
+// vector-unit launch (0.325 vs 0.275 ms for 64 matrices of N = 256): every warp re-read the whole chunk of V in both
+// sweeps and the per-chunk barriers left the light column groups waiting for the heavy one.  The ROW-distributed
+// version below loads each V fragment once per row block for all column groups and sheds dead rows evenly: 0.215 ms.
 #include <cooperative_groups.h>
 
 #include "sla_cta.cuh"
@@ -32,21 +31,30 @@ namespace sla {
 
 namespace {
 
-constexpr int OQ_THREADS = 256;   // 8 warps: one group of 8 columns each
+constexpr int OQ_THREADS = 256;   // 8 warps
 constexpr int OQ_LDV = 264;       // row stride of a reflector in the ring: = 8 (mod 16) doubles -> the 16-byte B loads of
                                   // the Z sweep are bank-conflict free
 constexpr int OQ_RING = 2 * 8 * OQ_LDV;
-// (the update sweep's loads are 4-way bank-conflicted with this stride; an XOR row swizzle that removes the conflicts
-// cost more in index math than it saved: 0.335 vs 0.325 ms)
-__device__ __forceinline__ int oq_swz(int) { return 0; }
-constexpr size_t OQ_SMEM = (size_t)(OQ_RING + 8 * 64 + 8 * 64 + 256) * sizeof(double) + 64;
+// Row swizzle of the ring: reflectors 2,3,6,7 of a chunk store row r at r ^ 8, so that the Z sweep (lanes = reflector
+// fi, 16 bytes each) AND the update sweep (lanes = reflector 2 fk + kk, 8 consecutive rows) both need the minimal
+// number of wavefronts (the update sweep is 4-way conflicted without it).
+__device__ __forceinline__ int oq_swz(int j) { return ((j >> 1) & 1) << 3; }
+// ring | partial Z^T [8 warps][8 groups][32 lanes][2] | partial G [8][64] | T [8 warps][64] | Y^T [8 groups][32][2] | taus
+constexpr size_t OQ_SMEM = (size_t)(OQ_RING + 8 * 8 * 64 + 8 * 64 + 8 * 64 + 8 * 64 + 256) * sizeof(double) + 64;
 
+// ROW-DISTRIBUTED: warp w owns the row blocks s = w, w+8, w+16, w+24 (8 rows each) of ALL 64 columns of its CTA
+// (8 column groups).  A V fragment is then loaded once per row block and used for every column group (a warp that
+// owns columns re-reads the whole chunk of V: that version was bound by shared-memory traffic and by the barrier
+// imbalance between heavy and light column groups), the dead rows (< k0) are shed evenly by all warps, and the
+// price is one reduction of the partial Z^T through shared memory per chunk (warp g finishes column group g).
 __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* const ring = reinterpret_cast<double*>(smem_raw);   // [2][8][OQ_LDV]
-    double* const Gp = ring + OQ_RING;                          // [8 warps][64] partial Gram matrices
+    double* const Zp = ring + OQ_RING;                          // [8 warps][8 groups][32 lanes][2]
+    double* const Gp = Zp + 8 * 8 * 64;                         // [8 warps][64] partial Gram matrices
     double* const Tw = Gp + 8 * 64;                             // [8 warps][64]  T (row-major), one private copy per warp
-    double* const taus = Tw + 8 * 64;                           // [256]
+    double* const Ys = Tw + 8 * 64;                             // [8 groups][32 lanes][2]
+    double* const taus = Ys + 8 * 64;                           // [256]
 
     const int n = p.n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -56,20 +64,21 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
     double* Lg = p.L + (long long)b * p.strideL;
     const int ldl = p.ldl;
     const double* tau_g = p.Twork + (long long)b * p.strideT;
-    // column groups: group g holds columns [32 g, 32 g + 32); the work grows with g (column c is touched by the
-    // reflectors k <= c), warps w and w + 4 share an SM sub-partition -> pair a heavy group with a light one.
-    // (Spreading a warp's columns over the whole range balances the warps but was slower: 0.385 vs 0.325 ms.)
-    const int g = (warp < 4) ? 7 - warp : warp - 4;
-    const int c = 32 * g + 4 * fi + rank;   // this lane's column of Q
 
     for (int r = tid; r < 256; r += OQ_THREADS) taus[r] = (r < n) ? tau_g[r] : 0.0;
     for (int r = tid; r < OQ_RING; r += OQ_THREADS) ring[r] = 0.0;   // rows >= n stay zero for ever
 
-    double Qt[32][2];
+    // lane (fi, fk) holds Q[row = 8 (warp + 8 i) + 2 fk + e][col = 32 g + 4 fi + rank]
+    double Qt[8][4][2];
 #pragma unroll
-    for (int s = 0; s < 32; ++s) {
-        Qt[s][0] = (8 * s + 2 * fk == c && c < n) ? 1.0 : 0.0;
-        Qt[s][1] = (8 * s + 2 * fk + 1 == c && c < n) ? 1.0 : 0.0;
+    for (int g = 0; g < 8; ++g) {
+        const int c = 32 * g + 4 * fi + rank;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = 8 * (warp + 8 * i) + 2 * fk;
+            Qt[g][i][0] = (r == c && c < n) ? 1.0 : 0.0;
+            Qt[g][i][1] = (r + 1 == c && c < n) ? 1.0 : 0.0;
+        }
     }
     __syncthreads();
 
@@ -92,38 +101,67 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
 
     for (int ch = nchunk - 1; ch >= 0; --ch) {
         cp_async_wait<0>();
-        __syncthreads();   // chunk ch has landed; everybody is done with chunk ch + 1 (the other buffer)
+        __syncthreads();   // chunk ch has landed; everybody is done with chunk ch + 1 (the other buffer, Zp, Ys)
         if (ch > 0) load_chunk(ch - 1, (ch - 1) & 1);
         const double* vb = ring + (size_t)(ch & 1) * 8 * OQ_LDV;
         const int k0 = ch * 8, kcnt = min(8, n - k0), s0 = ch;   // rows < k0 = 8 s0 are zero in every reflector of the chunk
-        // reflector j of the chunk, row k0 + r8 (only block s0 needs the mask): 0 above the diagonal, 1 on it;
-        // reflectors beyond n do not exist
+        const int g0 = k0 >> 5;                                  // column groups < g0 lie left of the chunk: untouched
+        // reflector j of the chunk, row k0 + r8 (only block s0 needs the mask): 0 above the diagonal, 1 on it
         auto masked = [&](double raw, int j, int r8) { return (r8 < j) ? 0.0 : (r8 == j ? 1.0 : raw); };
-        const bool jx_fi = fi < kcnt;   // reflector fi exists
+        const bool jx_fi = fi < kcnt;                            // reflector fi exists
+        const bool ja = 2 * fk < kcnt, jb = 2 * fk + 1 < kcnt;
+        const int swz_z = oq_swz(fi), swz_u = oq_swz(2 * fk);
 
-        // ---- Gram matrix G = V^T V: every warp sums a share of the row steps on the tensor core
+        // ---- partial Gram matrix and partial Z^T over this warp's live row blocks
         {
-            double g0 = 0.0, g1 = 0.0;
-            for (int t = 2 * s0 + warp; t < 64; t += 8) {
-                double x = vb[(size_t)fi * OQ_LDV + ((4 * t + fk) ^ oq_swz(fi))];
-                if (t < 2 * s0 + 2) x = masked(x, fi, 4 * t + fk - k0);
-                if (!jx_fi) x = 0.0;
-                dmma884(g0, g1, x, x);   // G[j = fi][j' = 2 fk + e]
+            double g0a = 0.0, g1a = 0.0;
+            double z[8][2];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) { z[g][0] = 0.0; z[g][1] = 0.0; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int sb = warp + 8 * i;
+                if (sb >= s0) {
+                    double2 vv = *reinterpret_cast<const double2*>(vb + (size_t)fi * OQ_LDV + ((8 * sb + 2 * fk) ^ swz_z));
+                    if (sb == s0) { vv.x = masked(vv.x, fi, 2 * fk); vv.y = masked(vv.y, fi, 2 * fk + 1); }
+                    if (!jx_fi) { vv.x = 0.0; vv.y = 0.0; }
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        if (g >= g0) {
+                            dmma884(z[g][0], z[g][1], Qt[g][i][0], vv.x);   // Z^T[col = fi][j = 2 fk + e]
+                            dmma884(z[g][0], z[g][1], Qt[g][i][1], vv.y);
+                        }
+                    // Gram: rows 8 sb + {fk, 4 + fk} of reflector fi against themselves
+                    double x0 = vb[(size_t)fi * OQ_LDV + ((8 * sb + fk) ^ swz_z)];
+                    double x1 = vb[(size_t)fi * OQ_LDV + ((8 * sb + 4 + fk) ^ swz_z)];
+                    if (sb == s0) { x0 = masked(x0, fi, fk); x1 = masked(x1, fi, 4 + fk); }
+                    if (!jx_fi) { x0 = 0.0; x1 = 0.0; }
+                    dmma884(g0a, g1a, x0, x0);   // G[j = fi][j' = 2 fk + e]
+                    dmma884(g0a, g1a, x1, x1);
+                }
             }
-            Gp[warp * 64 + fi * 8 + 2 * fk] = g0;
-            Gp[warp * 64 + fi * 8 + 2 * fk + 1] = g1;
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                if (g >= g0) *reinterpret_cast<double2*>(Zp + ((size_t)(warp * 8 + g) * 32 + lane) * 2) = make_double2(z[g][0], z[g][1]);
+            Gp[warp * 64 + fi * 8 + 2 * fk] = g0a;
+            Gp[warp * 64 + fi * 8 + 2 * fk + 1] = g1a;
         }
         __syncthreads();
-        if (32 * g + 31 < k0) continue;   // none of this warp's columns is touched by the chunk (warp-uniform)
 
-        // ---- T (forward, column-wise ?larft) -- every active warp builds its own copy (no second block barrier)
-        double* const Tm = Tw + warp * 64;
-        {
+        // ---- warp g finishes column group g: Z^T = sum of the partials, T, Y^T = Z^T T^T
+        if (warp >= g0) {
+            double* const Tm = Tw + warp * 64;
             double gs0 = 0.0, gs1 = 0.0;   // entries lane and lane + 32 of G
 #pragma unroll
             for (int w = 0; w < 8; ++w) { gs0 += Gp[w * 64 + lane]; gs1 += Gp[w * 64 + 32 + lane]; }
             Tm[lane] = gs0;                // G staged in the T buffer, turned into T row by row below
             Tm[32 + lane] = gs1;
+            double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const double2 zp = *reinterpret_cast<const double2*>(Zp + ((size_t)(w * 8 + warp) * 32 + lane) * 2);
+                z0 += zp.x; z1 += zp.y;
+            }
             __syncwarp();
             double Trow[8];
             if (lane < 8) {                // lane i builds row i of T:  T(i,j) = -tau_j sum_{l=i}^{j-1} T(i,l) G(l,j)
@@ -148,63 +186,60 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
                 for (int j = 0; j < 8; ++j) Tm[lane * 8 + j] = Trow[j];
             }
             __syncwarp();
-        }
-
-        // ---- Z^T = Q^T V over the rows >= k0
-        // (four independent accumulator pairs: a single DMMA accumulation chain would be latency-bound)
-        double za[4][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { za[i][0] = 0.0; za[i][1] = 0.0; }
-#pragma unroll
-        for (int s = 0; s < 32; ++s) {
-            if (s >= s0) {
-                double2 vv = *reinterpret_cast<const double2*>(vb + (size_t)fi * OQ_LDV + ((8 * s + 2 * fk) ^ oq_swz(fi)));
-                if (s == s0) { vv.x = masked(vv.x, fi, 2 * fk); vv.y = masked(vv.y, fi, 2 * fk + 1); }
-                if (!jx_fi) { vv.x = 0.0; vv.y = 0.0; }
-                dmma884(za[(2 * s) & 3][0], za[(2 * s) & 3][1], Qt[s][0], vv.x);   // Z^T[col = fi][j = 2 fk + e]
-                dmma884(za[(2 * s + 1) & 3][0], za[(2 * s + 1) & 3][1], Qt[s][1], vv.y);
-            }
-        }
-        const double z0 = (za[0][0] + za[1][0]) + (za[2][0] + za[3][0]);
-        const double z1 = (za[0][1] + za[1][1]) + (za[2][1] + za[3][1]);
-        // ---- Y^T = Z^T T^T   (k slot (fk, kk) <-> i = 2 fk + kk: the fragment as it came out)
-        double y0 = 0.0, y1 = 0.0;
-        {
+            // Y^T = Z^T T^T   (k slot (fk, kk) <-> i = 2 fk + kk: the fragment as it came out)
+            double y0 = 0.0, y1 = 0.0;
             const double2 t2 = *reinterpret_cast<const double2*>(Tm + fi * 8 + 2 * fk);   // T[j = fi][i = 2 fk + {0,1}]
             dmma884(y0, y1, z0, t2.x);
             dmma884(y0, y1, z1, t2.y);
+            *reinterpret_cast<double2*>(Ys + ((size_t)warp * 32 + lane) * 2) = make_double2(-y0, -y1);
         }
-        // ---- Q^T -= Y^T V^T   (k slot (fk, kk) <-> j = 2 fk + kk), straight into the Q fragments
+        __syncthreads();
+
+        // ---- Q^T -= Y^T V^T on this warp's live row blocks, every live column group (k slot <-> j = 2 fk + kk)
         {
-            const double ny0 = -y0, ny1 = -y1;
-            const double* va = vb + (size_t)(2 * fk) * OQ_LDV + fi;
-            const int swz = oq_swz(2 * fk);   // the same for reflectors 2 fk and 2 fk + 1
-            const bool ja = 2 * fk < kcnt, jb = 2 * fk + 1 < kcnt;
+            double ny[8][2];
 #pragma unroll
-            for (int s = 0; s < 32; ++s) {
-                if (s >= s0) {
-                    double b0 = va[(8 * s) ^ swz], b1 = va[OQ_LDV + ((8 * s) ^ swz)];
-                    if (s == s0) { b0 = masked(b0, 2 * fk, fi); b1 = masked(b1, 2 * fk + 1, fi); }
+            for (int g = 0; g < 8; ++g)
+                if (g >= g0) {
+                    const double2 y2 = *reinterpret_cast<const double2*>(Ys + ((size_t)g * 32 + lane) * 2);
+                    ny[g][0] = y2.x; ny[g][1] = y2.y;
+                } else { ny[g][0] = 0.0; ny[g][1] = 0.0; }
+            const double* const va = vb + (size_t)(2 * fk) * OQ_LDV + fi;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int sb = warp + 8 * i;
+                if (sb >= s0) {
+                    double b0 = va[(8 * sb) ^ swz_u], b1 = va[OQ_LDV + ((8 * sb) ^ swz_u)];
+                    if (sb == s0) { b0 = masked(b0, 2 * fk, fi); b1 = masked(b1, 2 * fk + 1, fi); }
                     if (!ja) b0 = 0.0;
                     if (!jb) b1 = 0.0;
-                    dmma884(Qt[s][0], Qt[s][1], ny0, b0);
-                    dmma884(Qt[s][0], Qt[s][1], ny1, b1);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        if (g >= g0) {
+                            dmma884(Qt[g][i][0], Qt[g][i][1], ny[g][0], b0);
+                            dmma884(Qt[g][i][0], Qt[g][i][1], ny[g][1], b1);
+                        }
                 }
             }
         }
     }
     cg::this_cluster().sync();   // every CTA of the matrix is done reading the reflectors from L
 
-    if (c < n) {
-        double* dst = Lg + (long long)c * ldl;
+    {
         const bool v2 = (((size_t)ldl * sizeof(double)) % 16 == 0) && ((((uintptr_t)Lg) & 15) == 0);
 #pragma unroll
-        for (int s = 0; s < 32; ++s) {
-            const int r = 8 * s + 2 * fk;
-            if (v2 && r + 1 < n) *reinterpret_cast<double2*>(dst + r) = make_double2(Qt[s][0], Qt[s][1]);
-            else {
-                if (r < n) dst[r] = Qt[s][0];
-                if (r + 1 < n) dst[r + 1] = Qt[s][1];
+        for (int g = 0; g < 8; ++g) {
+            const int c = 32 * g + 4 * fi + rank;
+            if (c >= n) continue;
+            double* dst = Lg + (long long)c * ldl;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 8 * (warp + 8 * i) + 2 * fk;
+                if (v2 && r + 1 < n) *reinterpret_cast<double2*>(dst + r) = make_double2(Qt[g][i][0], Qt[g][i][1]);
+                else {
+                    if (r < n) dst[r] = Qt[g][i][0];
+                    if (r + 1 < n) dst[r + 1] = Qt[g][i][1];
+                }
             }
         }
     }

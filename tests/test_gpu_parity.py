@@ -550,7 +550,7 @@ def test_ldr_hybrid_shape_edge_inputs(S):
             assert relerr((L[b] * d[b][None, :]) @ R[b], B[b]) < 1e-12
 
 
-@pytest.mark.parametrize("algo", ["streaming", "cluster", "hyb", "hyb+oneq", "hyb+qdmma"])
+@pytest.mark.parametrize("algo", ["streaming", "cluster", "hyb", "hyb+oneq", "hyb+qvec"])
 def test_other_ldr_kernels_subprocess(algo):
     """Default LDR kernel for n <= 256 is the register-resident cluster kernel.  The shared-memory cluster
     kernel (256 < n <= 512, e.g. C5's N=400) and the L2-streaming kernel (larger n, e.g. C4's N=1024) are
@@ -563,8 +563,8 @@ def test_other_ldr_kernels_subprocess(algo):
     env = dict(os.environ, SLA_LDR_ALGO=algo.split("+")[0])
     if algo.endswith("+oneq"):    # the hybrid shape with Q formed in the same launch (MODE 0) instead of a second one
         env["SLA_HYB_SPLITQ"] = "0"
-    if algo.endswith("+qdmma"):   # Q formed on the FP64 tensor cores (sla_orgq.cu, off by default)
-        env["SLA_Q_DMMA"] = "1"
+    if algo.endswith("+qvec"):    # Q formed by the vector-unit MODE 2 launch instead of the tensor-core kernel (sla_orgq.cu)
+        env["SLA_Q_DMMA"] = "0"
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
                         "ldr_random or ldr_graded or ldr_identity or ldr_hybrid or chain_C1 or ref_lmul_matrix or small_complex"],
                        env=env, capture_output=True, text=True, timeout=900)
