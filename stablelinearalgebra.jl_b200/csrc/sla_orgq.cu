@@ -39,8 +39,8 @@ constexpr int OQ_RING = 2 * 8 * OQ_LDV;
 // fi, 16 bytes each) AND the update sweep (lanes = reflector 2 fk + kk, 8 consecutive rows) both need the minimal
 // number of wavefronts (the update sweep is 4-way conflicted without it).
 __device__ __forceinline__ int oq_swz(int j) { return ((j >> 1) & 1) << 3; }
-// ring | partial Z^T [8 warps][8 groups][32 lanes][2] | partial G [8][64] | T [8 warps][64] | Y^T [8 groups][32][2] | taus
-constexpr size_t OQ_SMEM = (size_t)(OQ_RING + 8 * 8 * 64 + 8 * 64 + 8 * 64 + 8 * 64 + 256) * sizeof(double) + 64;
+// ring | partial Z^T [8 warps][8 groups][32 lanes][2] | T of every chunk [32][64] | scratch [8 warps][64] | Y^T [8 groups][32][2] | taus
+constexpr size_t OQ_SMEM = (size_t)(OQ_RING + 8 * 8 * 64 + 32 * 64 + 8 * 64 + 8 * 64 + 256) * sizeof(double) + 64;
 
 // ROW-DISTRIBUTED: warp w owns the row blocks s = w, w+8, w+16, w+24 (8 rows each) of ALL 64 columns of its CTA
 // (8 column groups).  A V fragment is then loaded once per row block and used for every column group (a warp that
@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* const ring = reinterpret_cast<double*>(smem_raw);   // [2][8][OQ_LDV]
     double* const Zp = ring + OQ_RING;                          // [8 warps][8 groups][32 lanes][2]
-    double* const Gp = Zp + 8 * 8 * 64;                         // [8 warps][64] partial Gram matrices
-    double* const Tw = Gp + 8 * 64;                             // [8 warps][64]  T (row-major), one private copy per warp
+    double* const Tall = Zp + 8 * 8 * 64;                       // [32 chunks][64]  T of every chunk (row-major)
+    double* const Tw = Tall + 32 * 64;                          // [8 warps][64]  scratch of the T prologue
     double* const Ys = Tw + 8 * 64;                             // [8 groups][32 lanes][2]
     double* const taus = Ys + 8 * 64;                           // [256]
 
@@ -83,6 +83,44 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
     __syncthreads();
 
     const int nchunk = (n + 7) / 8;
+    // ---- prologue: T of EVERY chunk (they depend on V only), four chunks per warp, straight from global memory:
+    // G = V^T V on the tensor core, then the ?larft recurrence on 8 lanes -- off the per-chunk critical path
+    for (int cq = warp; cq < nchunk; cq += 8) {
+        const int k0 = cq * 8, kj = k0 + fi;           // lane's reflector (column kj of L)
+        const double* col = Lg + (long long)kj * ldl;
+        double g0a = 0.0, g1a = 0.0, g0b = 0.0, g1b = 0.0;
+        for (int t = 2 * cq; t < 64; t += 2) {         // two independent accumulation chains
+            const int r0 = 4 * t + fk, r1 = r0 + 4;
+            double x0 = (kj < n && r0 < n && r0 > kj) ? col[r0] : ((r0 == kj && kj < n) ? 1.0 : 0.0);
+            double x1 = (kj < n && r1 < n && r1 > kj) ? col[r1] : ((r1 == kj && kj < n) ? 1.0 : 0.0);
+            dmma884(g0a, g1a, x0, x0);                 // G[j = fi][j' = 2 fk + e]
+            dmma884(g0b, g1b, x1, x1);
+        }
+        double* const Gm = Tw + warp * 64;
+        Gm[fi * 8 + 2 * fk] = g0a + g0b;
+        Gm[fi * 8 + 2 * fk + 1] = g1a + g1b;
+        __syncwarp();
+        double Trow[8];
+        if (lane < 8) {                                // lane i builds row i of T:  T(i,j) = -tau_j sum_{l=i}^{j-1} T(i,l) G(l,j)
+            const int i = lane;
+            const double ti = taus[k0 + i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Trow[j] = (j == i) ? ti : 0.0;
+#pragma unroll
+            for (int j = 1; j < 8; ++j) {
+                if (j > i) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int l = 0; l < 8; ++l)
+                        if (l >= i && l < j) acc = fma(Trow[l], Gm[l * 8 + j], acc);
+                    Trow[j] = -taus[k0 + j] * acc;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Tall[cq * 64 + i * 8 + j] = Trow[j];
+        }
+        __syncwarp();
+    }
     const bool vecq = (((size_t)ldl * sizeof(double)) % 16 == 0) && ((((uintptr_t)Lg) & 15) == 0) && (n % 2 == 0);
     auto load_chunk = [&](int ch, int buf) {   // 32 threads per reflector
         const int i = tid >> 5, k = ch * 8 + i;
@@ -112,9 +150,8 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
         const bool ja = 2 * fk < kcnt, jb = 2 * fk + 1 < kcnt;
         const int swz_z = oq_swz(fi), swz_u = oq_swz(2 * fk);
 
-        // ---- partial Gram matrix and partial Z^T over this warp's live row blocks
+        // ---- partial Z^T over this warp's live row blocks
         {
-            double g0a = 0.0, g1a = 0.0;
             double z[8][2];
 #pragma unroll
             for (int g = 0; g < 8; ++g) { z[g][0] = 0.0; z[g][1] = 0.0; }
@@ -131,61 +168,23 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
                             dmma884(z[g][0], z[g][1], Qt[g][i][0], vv.x);   // Z^T[col = fi][j = 2 fk + e]
                             dmma884(z[g][0], z[g][1], Qt[g][i][1], vv.y);
                         }
-                    // Gram: rows 8 sb + {fk, 4 + fk} of reflector fi against themselves
-                    double x0 = vb[(size_t)fi * OQ_LDV + ((8 * sb + fk) ^ swz_z)];
-                    double x1 = vb[(size_t)fi * OQ_LDV + ((8 * sb + 4 + fk) ^ swz_z)];
-                    if (sb == s0) { x0 = masked(x0, fi, fk); x1 = masked(x1, fi, 4 + fk); }
-                    if (!jx_fi) { x0 = 0.0; x1 = 0.0; }
-                    dmma884(g0a, g1a, x0, x0);   // G[j = fi][j' = 2 fk + e]
-                    dmma884(g0a, g1a, x1, x1);
                 }
             }
 #pragma unroll
             for (int g = 0; g < 8; ++g)
                 if (g >= g0) *reinterpret_cast<double2*>(Zp + ((size_t)(warp * 8 + g) * 32 + lane) * 2) = make_double2(z[g][0], z[g][1]);
-            Gp[warp * 64 + fi * 8 + 2 * fk] = g0a;
-            Gp[warp * 64 + fi * 8 + 2 * fk + 1] = g1a;
         }
         __syncthreads();
 
         // ---- warp g finishes column group g: Z^T = sum of the partials, T, Y^T = Z^T T^T
         if (warp >= g0) {
-            double* const Tm = Tw + warp * 64;
-            double gs0 = 0.0, gs1 = 0.0;   // entries lane and lane + 32 of G
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { gs0 += Gp[w * 64 + lane]; gs1 += Gp[w * 64 + 32 + lane]; }
-            Tm[lane] = gs0;                // G staged in the T buffer, turned into T row by row below
-            Tm[32 + lane] = gs1;
+            const double* const Tm = Tall + ch * 64;   // from the prologue
             double z0 = 0.0, z1 = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
                 const double2 zp = *reinterpret_cast<const double2*>(Zp + ((size_t)(w * 8 + warp) * 32 + lane) * 2);
                 z0 += zp.x; z1 += zp.y;
             }
-            __syncwarp();
-            double Trow[8];
-            if (lane < 8) {                // lane i builds row i of T:  T(i,j) = -tau_j sum_{l=i}^{j-1} T(i,l) G(l,j)
-                const int i = lane;
-                const double ti = taus[k0 + i];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) Trow[j] = (j == i) ? ti : 0.0;
-#pragma unroll
-                for (int j = 1; j < 8; ++j) {
-                    if (j > i) {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int l = 0; l < 8; ++l)
-                            if (l >= i && l < j) acc = fma(Trow[l], Tm[l * 8 + j], acc);
-                        Trow[j] = -taus[k0 + j] * acc;
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane < 8) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) Tm[lane * 8 + j] = Trow[j];
-            }
-            __syncwarp();
             // Y^T = Z^T T^T   (k slot (fk, kk) <-> i = 2 fk + kk: the fragment as it came out)
             double y0 = 0.0, y1 = 0.0;
             const double2 t2 = *reinterpret_cast<const double2*>(Tm + fi * 8 + 2 * fk);   // T[j = fi][i = 2 fk + {0,1}]
