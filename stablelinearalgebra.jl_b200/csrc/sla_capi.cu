@@ -145,15 +145,16 @@ template <typename T> struct Ctx {
         const bool reg_pays = cs_reg > 0 && waves(batch, 132 / cs_reg) <= 4 * w_stream;
         const bool cl_pays = cs_cl > 0 && 2 * waves(batch, 132 / cs_cl) <= 5 * w_stream;
         // 128 < n <= 256, real: the hybrid shape (half the matrix in shared memory, clusters of 2) holds twice as many
-        // matrices.  Its factorisation wave costs what a register-shape wave costs (0.73 ms at N=256) and Q is then
-        // formed by register-shape waves of 0.14 ms: t_hyb = 0.73 w_hyb + 0.14 w_reg vs t_reg = 0.73 w_reg, i.e. the
-        // hybrid path wins when w_hyb < 0.81 w_reg (64 chains: 1 wave instead of 2).  SLA_LDR_ALGO=hyb forces it.
+        // matrices.  Measured at N=256: register-shape factorisation wave 0.56 ms, hybrid wave 0.71 ms, Q formation
+        // (tensor cores, clusters of 4) 0.095 ms per register-shape wave: t_reg = 0.656 w_reg, t_hyb = 0.71 w_hyb +
+        // 0.095 w_reg, i.e. the hybrid path wins when w_hyb < 0.79 w_reg (64 chains: 1 wave instead of 2).
+        // SLA_LDR_ALGO=hyb forces it.
         const int cs_hyb = ldr_hyb_cluster_size<T>(n);
         bool hyb_pays = false;
         if (cs_hyb > 0 && forced == 0 && reg_pays) {
             int c_reg = 0, c_hyb = 0;
             ldr_n256_resident(&c_reg, &c_hyb);
-            if (c_reg > 0 && c_hyb > 0) hyb_pays = 100 * waves(batch, c_hyb) < 81 * waves(batch, c_reg);
+            if (c_reg > 0 && c_hyb > 0) hyb_pays = 100 * waves(batch, c_hyb) < 79 * waves(batch, c_reg);
         }
         if (cs_hyb > 0 && (forced == 4 || hyb_pays)) CK(ldr_hyb_batched<T>(a, s));
         else if (forced == 1 ? cs_reg > 0 : (forced == 0 && reg_pays)) CK(ldr_reg_batched<T>(a, s));

@@ -1033,7 +1033,17 @@ template <> cudaError_t ldr_reg_batched<double>(const LdrArgs<double>& p, cudaSt
     if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
     if (p.n <= 64) return launch_reg<double, 1, 2, 4>(p, s);
     if (p.n <= 128) return launch_reg<double, 1, 4, 8>(p, s);
-    if (p.n <= 256) return launch_reg<double, 4, 8, 4>(p, s);
+    if (p.n <= 256) {
+        // 128 < n <= 256: factorise (MODE 1), then form Q on the tensor cores (sla_orgq.cu); SLA_Q_DMMA=0 or no tau
+        // workspace: everything in one launch (MODE 0)
+        static const bool qdmma = !(getenv("SLA_Q_DMMA") && atoi(getenv("SLA_Q_DMMA")) == 0);
+        if (qdmma && p.Twork != nullptr && p.strideT >= p.n) {
+            cudaError_t e = launch_reg<double, 4, 8, 4, 0, 1>(p, s);
+            if (e != cudaSuccess) return e;
+            return orgq_dmma_batched(p, s);
+        }
+        return launch_reg<double, 4, 8, 4>(p, s);
+    }
     return cudaErrorNotSupported;
 }
 template <> cudaError_t ldr_reg_batched<cplx>(const LdrArgs<cplx>& p, cudaStream_t s) {
