@@ -1,16 +1,17 @@
 #!/usr/bin/env python
 """Benchmark of the stabilised G(tau=0) hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--config C2] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--config C1|C2|C3|C4|C5] [--scaling weak|strong] [--impl reference]
 
 A *step* is one pass of the hot path over one batch of chains: for every chain, L slices of
 Hubbard-like B matrices, re-factorised every n_stab=10 slices (lmul! -> ldr!), then inv_IpA!
 (inv_IpUV! for the complex config) -> G, log|det G|, sign.  `value` = evaluations/s with the inputs
 already resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` = the same
 metric through the public host API with HOST (pinned) buffers, host<->device copies inside the timed
-region.  Multi-GPU: the batch of chains is sharded, each rank runs `chains` chains of its own (weak
-scaling) and a single small NCCL all-reduce per step combines the cross-walker sums of log|det| and
-sign.  `--impl reference` times the CPU restatement of the reference (oracle/, C over ILP64 OpenBLAS
+region (the device->host read of step k overlaps the computation of step k+1 on a copy stream, double-buffered
+outputs).  Multi-GPU: the batch of chains is sharded -- `--scaling weak` (default): each rank runs the config's
+per-GPU share of chains (C5: 512); `--scaling strong`: the config's TOTAL number of chains (C5: 4096) is split over
+the ranks -- and a single small NCCL all-reduce per step combines the cross-walker sums of log|det| and sign.  `--impl reference` times the CPU restatement of the reference (oracle/, C over ILP64 OpenBLAS
 LAPACK; Julia is not installable here) on all host cores, one chain per thread, 1 BLAS thread each.
 The oracle is executed in exactly two places: that reference arm and the `cpu_baseline` leg (rank 0, one GPU); the
 `parity` key compares the GPU results of chains 0..1 with the results the cpu_baseline leg computed for the same chains.
@@ -36,21 +37,37 @@ METRIC = "stabilised G(tau=0) evals/sec"
 UNIT = "evals/s"
 
 
-def get_cfg(name, chains=None):
+# chains per GPU under weak scaling where it differs from the config's total (BASELINE: "4096 chains ... sharded over
+# 1/2/4/8 B200" = 512 per GPU at 8 GPUs); every other config's batch is its per-GPU share
+WEAK_CHAINS_PER_GPU = {"C5": 512}
+DEFAULT_STEPS = {"C1": 50, "C2": 20, "C3": 10, "C4": 3, "C5": 5}
+
+
+def get_cfg(name, chains=None, scaling="weak", world=1, rank=0):
+    """The workload of this rank: (config with .chains = chains of THIS rank, global chain ids, total chains)."""
     import sla_b200
-    cfg = sla_b200.synthetic.CONFIGS[name]
-    if chains is not None:
-        syn = sla_b200.synthetic
-        cfg = syn.HubbardConfig(cfg.name, cfg.Lx, cfg.L, cfg.n_stab, chains, dtype=cfg.dtype, U=cfg.U, dtau=cfg.dtau,
-                                mu=cfg.mu, phase=cfg.phase, inverse=cfg.inverse)
-    return cfg
+    from sla_b200 import walkers
+    syn = sla_b200.synthetic
+    base = syn.CONFIGS[name]
+    if scaling == "strong":
+        total = chains if chains is not None else base.chains
+        ids = walkers.shard_chains(total, world, rank)
+    else:
+        per = chains if chains is not None else WEAK_CHAINS_PER_GPU.get(name, base.chains)
+        total = per * world
+        ids = walkers.weak_chain_ids(per, rank)
+    cfg = syn.HubbardConfig(base.name, base.Lx, base.L, base.n_stab, len(ids), dtype=base.dtype, U=base.U,
+                            dtau=base.dtau, mu=base.mu, phase=base.phase, inverse=base.inverse)
+    return cfg, ids, total
 
 
-def config_json(cfg, n_gpus, extra=None):
-    c = {"workload": f"{cfg.name}: {cfg.chains} chains/GPU, N={cfg.N} ({cfg.Lx}x{cfg.Lx} Hubbard, U={cfg.U}, "
+def config_json(cfg, n_gpus, extra=None, total=None, scaling="weak"):
+    total = cfg.chains * n_gpus if total is None else total
+    c = {"workload": f"{cfg.name}: {total} chains over {n_gpus} GPU(s) ({scaling} scaling, {cfg.chains} on rank 0), "
+                     f"N={cfg.N} ({cfg.Lx}x{cfg.Lx} Hubbard, U={cfg.U}, "
                      f"dtau={cfg.dtau}), L={cfg.L}, n_stab={cfg.n_stab}, inv_{cfg.inverse}!",
          "N": cfg.N, "L": cfg.L, "n_stab": cfg.n_stab, "chains_per_gpu": cfg.chains,
-         "chains_total": cfg.chains * n_gpus, "eltype": "ComplexF64" if cfg.dtype.kind == "c" else "Float64",
+         "chains_total": total, "eltype": "ComplexF64" if cfg.dtype.kind == "c" else "Float64",
          "inverse": "inv_" + cfg.inverse + "!", "parallelism": f"chains sharded over {n_gpus} GPU(s)",
          "flops_per_eval": cfg.flops_per_eval()}
     if extra:
@@ -61,40 +78,59 @@ def config_json(cfg, n_gpus, extra=None):
 # ----------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle's C restatement on the host cores
 # ----------------------------------------------------------------------------------------------------
-def cpu_run(cfg, chains, threads, keep=0):
+def cpu_run(cfg, chains, threads, keep=0, blas_threads=1):
     """Time the CPU arm on chains 0..chains-1; with `keep` also return (G, logdet, sign) of the first `keep` chains."""
     from oracle import c_oracle
     expK = cfg.expK()
     fields = cfg.fields(range(chains))
     t0 = time.perf_counter()
-    G, ld, sg = c_oracle.eval_batch(expK, fields, cfg.lam, cfg.n_stab, cfg.inverse, nthreads=threads)
+    G, ld, sg = c_oracle.eval_batch(expK, fields, cfg.lam, cfg.n_stab, cfg.inverse, nthreads=threads,
+                                    blas_threads=blas_threads)
     t = time.perf_counter() - t0
     return (t, (G[:keep], ld[:keep], sg[:keep])) if keep else t
+
+
+def host_cores():
+    """(logical CPUs this process may use, physical cores of the box)."""
+    logical = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False) or logical
+    except Exception:
+        physical = logical
+    return logical, physical
 
 
 def cpu_baseline(cfg, budget_s=12.0, keep=2):
     """The cpu_baseline leg.  Its first pass evaluates chains 0..cores-1 -- the ids rank 0 evaluates on the GPU -- so the
     results of the first `keep` chains double as the parity check of the line (no second run of the oracle)."""
     from oracle import c_oracle
-    cores = os.cpu_count() or 1
+    cores, physical = host_cores()
     keep = min(keep, cores)
     t1, ref = cpu_run(cfg, cores, cores, keep=keep)      # one chain per core
     rounds = max(1, min(8, int(budget_s / max(t1, 1e-3))))
     chains = cores * rounds
     t = cpu_run(cfg, chains, cores) if rounds > 1 else t1
-    return {"value": chains / t, "unit": UNIT, "cores": cores, "kind": "port",
+    # for transparency (SURVEY 8(d)): the other arrangement, ONE worker x all BLAS threads, on a short sample
+    n2 = 2 if t1 < 4.0 else 1
+    t2 = cpu_run(cfg, n2, 1, blas_threads=cores)
+    return {"value": chains / t, "unit": UNIT, "cores": cores, "physical_cores": physical, "kind": "port",
             "sample": f"{chains} chains of the same workload ({cfg.name} size), {cores} worker threads x 1 BLAS "
-                      f"thread, {t:.2f} s wall; C restatement of the reference over {c_oracle.blas_config()}"}, ref
+                      f"thread, {t:.2f} s wall; C restatement of the reference over {c_oracle.blas_config()}",
+            "secondary": {"value": n2 / t2, "unit": UNIT, "arrangement": f"1 worker x {cores} BLAS threads",
+                          "sample": f"{n2} chain(s), {t2:.2f} s wall"}}, ref
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = get_cfg(args.config, args.chains)
-    cores = os.cpu_count() or 1
+    cfg, _, total = get_cfg(args.config, args.chains, args.scaling, max(args.gpus, 1), 0)
+    cores, physical = host_cores()
     from oracle import c_oracle
     chains = cores  # bounded sample per step: one chain per host thread
+    if args.steps is None:
+        args.steps = {"C1": 20, "C2": 5, "C3": 2, "C4": 1, "C5": 2}.get(cfg.name, 2)
     for _ in range(args.warmup):
         cpu_run(cfg, chains, cores)
     t0 = time.perf_counter()
@@ -102,13 +138,15 @@ def run_reference(args):
         cpu_run(cfg, chains, cores)
     t = time.perf_counter() - t0
     value = chains * args.steps / t
-    sample = (f"{chains} chains/step ({cfg.name} size), {cores} worker threads x 1 BLAS thread; "
+    sample = (f"{chains} chains/step ({cfg.name} size), {cores} worker threads ({physical} physical cores) x 1 BLAS thread; "
               f"LAPACK-level C restatement (Julia not installed); {c_oracle.blas_config()}")
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+           "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": args.scaling,
            "vs_baseline": None, "dtype": "c128" if cfg.dtype.kind == "c" else "f64", "data": "synthetic",
-           "config": config_json(cfg, args.gpus, {"cpu_sample_chains_per_step": chains}),
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "config": config_json(cfg, args.gpus, None, total, args.scaling),
+           "cpu_sample_chains_per_step": chains,
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "physical_cores": physical, "kind": "port",
+                            "sample": sample},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -178,9 +216,19 @@ def measure_dgemm_peak(torch, seconds=0.6):
     return best
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE group-product GEMM launch at the C2 shape (N=256, batch 128),
-# from the `ncu --set full` capture summarised in profiles/ncu_gemm_kernel_r1.txt
-NCU_GEMM_TRAFFIC_BYTES_C2 = 97.5e6
+def ncu_record(kernel, cfg_name):
+    """ncu-derived figures of a kernel (DRAM bytes per launch, tensor-pipe activity) from the COMMITTED summary
+    profiles/ncu_kernel_metrics.json, keyed by kernel and config; None when no capture of this build is recorded --
+    they are never constants in this file."""
+    path = os.path.join(ROOT, "profiles", "ncu_kernel_metrics.json")
+    try:
+        with open(path) as f:
+            for e in json.load(f)["entries"]:
+                if e["kernel"] == kernel and e["config"] == cfg_name:
+                    return e
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
 
 
 def measure_gemm_kernel(torch, sla, cfg, reps=20):
@@ -208,6 +256,29 @@ def measure_gemm_kernel(torch, sla, cfg, reps=20):
     return ms, flops, batch
 
 
+def measure_ldr_kernel(torch, sla, cfg, F, reps=10):
+    """Average duration of ONE ldr! (pivoted QR + R extraction + Q formation) of the whole batch on the kind of matrix
+    the chain hands it -- (L D) of the final factorisation: columns graded over the full range of d -- with CUDA
+    events; algorithmic work 8/3 N^3 per matrix (4/3 ?geqp3 + 4/3 ?orgqr), x4 complex."""
+    A = (F.L * F.d[:, :, None].to(F.L.dtype)).contiguous()     # column j of L scaled by d_j (column-major batch)
+    ws = sla.ldr_workspace(F)
+    W = sla.ldr(F)
+    for _ in range(2):
+        sla.ldr_(W, A, ws)
+    torch.cuda.synchronize()
+    l0 = sla.load().sla_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        sla.ldr_(W, A, ws)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    launches = (sla.load().sla_launch_count() - l0) // reps
+    flops = (4.0 if cfg.dtype.kind == "c" else 1.0) * (8.0 / 3.0) * cfg.N ** 3 * cfg.chains
+    return ms, flops, sla.last_ldr_algo(), int(launches)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -229,55 +300,72 @@ def run_gpu(args):
             _g.build()
     if world > 1:
         dist.barrier()
-    cfg = get_cfg(args.config, args.chains)
+    cfg, chain_ids, total_chains = get_cfg(args.config, args.chains, args.scaling, world, rank)
     n, L, chains = cfg.N, cfg.L, cfg.chains
     dt = torch.complex128 if cfg.dtype.kind == "c" else torch.float64
     from sla_b200 import walkers
-    chain_ids = walkers.weak_chain_ids(chains, rank)           # global chain ids: sharding-invariant fields
 
     expK_h = torch.from_numpy(np.ascontiguousarray(cfg.expK().T)).pin_memory()      # column-major storage
     fields_h = torch.from_numpy(cfg.fields(chain_ids)).pin_memory()
     expK_d = expK_h.cuda()[None]
     fields_d = fields_h.cuda()
-    G = torch.empty((chains, n, n), dtype=dt, device="cuda")
-    logdet = torch.empty(chains, dtype=torch.float64, device="cuda")
-    sign = torch.empty(chains, dtype=dt, device="cuda")
+    # outputs are double-buffered: the device->host read of step k runs on a copy stream while step k+1 computes
+    Gs = [torch.empty((chains, n, n), dtype=dt, device="cuda") for _ in range(2)]
+    logdets = [torch.empty(chains, dtype=torch.float64, device="cuda") for _ in range(2)]
+    signs = [torch.empty(chains, dtype=dt, device="cuda") for _ in range(2)]
+    accs = [torch.zeros(4, dtype=torch.float64, device="cuda") for _ in range(2)]
+    G, logdet, sign, acc = Gs[0], logdets[0], signs[0], accs[0]
     ws = torch.empty(sla.greens_chain_workspace_bytes(dt, n, chains, L, cfg.n_stab), dtype=torch.uint8, device="cuda")
-    G_h = torch.empty((chains, n, n), dtype=dt).pin_memory()
-    logdet_h = torch.empty(chains, dtype=torch.float64).pin_memory()
-    sign_h = torch.empty(chains, dtype=dt).pin_memory()
-    acc = torch.zeros(4, dtype=torch.float64, device="cuda")
+    G_hs = [torch.empty((chains, n, n), dtype=dt).pin_memory() for _ in range(2)]
+    logdet_hs = [torch.empty(chains, dtype=torch.float64).pin_memory() for _ in range(2)]
+    sign_hs = [torch.empty(chains, dtype=dt).pin_memory() for _ in range(2)]
+    acc_hs = [torch.empty(4, dtype=torch.float64).pin_memory() for _ in range(2)]
     lib = sla.load()
-
-    def reduce_walkers():
-        # cross-walker reduction of log-determinants and signs (the only collective on this path)
-        walkers.reduce_walkers(logdet, sign, out=acc)
+    copy_stream = torch.cuda.Stream()
+    ev_done = [torch.cuda.Event() for _ in range(2)]     # step's results complete on the compute stream
+    ev_read = [torch.cuda.Event() for _ in range(2)]     # step's results are in host memory
+    state = {"k": 0}
 
     def step_device():
         sla.greens_chain(expK_d, fields_d, cfg.lam, cfg.n_stab, cfg.inverse, G=G, logdet=logdet, sign=sign, ws=ws)
-        reduce_walkers()
+        # cross-walker reduction of log-determinants and signs: one library kernel + the only collective of the path
+        walkers.reduce_walkers(logdet, sign, out=acc)
 
     def step_e2e():
+        i = state["k"] & 1
+        state["k"] += 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev_read[i])                 # buffer set i was read out two steps ago
         ek = expK_h.to("cuda", non_blocking=True)[None]
         fd = fields_h.to("cuda", non_blocking=True)
-        sla.greens_chain(ek, fd, cfg.lam, cfg.n_stab, cfg.inverse, G=G, logdet=logdet, sign=sign, ws=ws)
-        reduce_walkers()
-        G_h.copy_(G, non_blocking=True)
-        logdet_h.copy_(logdet, non_blocking=True)
-        sign_h.copy_(sign, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        sla.greens_chain(ek, fd, cfg.lam, cfg.n_stab, cfg.inverse, G=Gs[i], logdet=logdets[i], sign=signs[i], ws=ws)
+        walkers.reduce_walkers(logdets[i], signs[i], out=accs[i])
+        ev_done[i].record(cur)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[i])
+            G_hs[i].copy_(Gs[i], non_blocking=True)
+            logdet_hs[i].copy_(logdets[i], non_blocking=True)
+            sign_hs[i].copy_(signs[i], non_blocking=True)
+            acc_hs[i].copy_(accs[i], non_blocking=True)
+            ev_read[i].record(copy_stream)
+
+    def e2e_drain():
+        copy_stream.synchronize()
+        torch.cuda.current_stream().wait_stream(copy_stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, drain=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if drain:
+            drain()                  # every step's results are in host memory before the clock stops
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -285,58 +373,92 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
+    steps = args.steps if args.steps is not None else DEFAULT_STEPS.get(cfg.name, 10)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_device()
     l0 = lib.sla_launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_total = timed(step_device, args.steps)
+    ms_total = timed(step_device, steps)
     clocks = sampler.stop() if sampler else None
-    launches = (lib.sla_launch_count() - l0) // args.steps
-    value = chains * world * args.steps / (ms_total * 1e-3)
+    launches = (lib.sla_launch_count() - l0) // steps
+    value = total_chains * steps / (ms_total * 1e-3)
+    ldr_algo = sla.last_ldr_algo()
 
-    step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    e2e_value = chains * world * args.steps / (ms_e2e * 1e-3)
+    for _ in range(2):
+        step_e2e()
+    e2e_drain()
+    ms_e2e = timed(step_e2e, steps, drain=e2e_drain)
+    e2e_value = total_chains * steps / (ms_e2e * 1e-3)
     h2d = expK_h.numel() * expK_h.element_size() + fields_h.numel()
-    d2h = sum(t.numel() * t.element_size() for t in (G_h, logdet_h, sign_h))
+    d2h = sum(t.numel() * t.element_size() for t in (G_hs[0], logdet_hs[0], sign_hs[0], acc_hs[0]))
+    last = (state["k"] - 1) & 1
+    G_h, logdet_h, sign_h = G_hs[last], logdet_hs[last], sign_hs[last]
 
     parity = None   # filled from the cpu_baseline leg below (rank 0, one GPU): same chain ids on both sides
 
-    roof = cpub = None
+    roof = roof_ldr = cpub = None
     if rank == 0:
         gm_ms, gm_flops, gm_batch = measure_gemm_kernel(torch, sla, cfg)
         peak = measure_dgemm_peak(torch)
         achieved = gm_flops / (gm_ms * 1e-3) / 1e12
+        step_tflops = cfg.flops_per_eval() * chains / (ms_total / steps * 1e-3) / 1e12
+        rec = ncu_record("gemm_kernel", cfg.name)
         roof = {"bound": "tensor", "kernel": "sla::gemm_kernel (batched FP64 DMMA GEMM, group-product shape)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": NCU_GEMM_TRAFFIC_BYTES_C2 if (cfg.N == 256 and cfg.chains == 64 and cfg.dtype.kind != "c") else None,
-                "traffic_unit": "bytes/launch (ncu dram read+write; algorithmic HBM bytes of the launch: 134.7e6)",
-                "dmma_pipe_active_pct_ncu": 81.3,
+                "traffic": rec["dram_bytes_per_launch"] if rec else None,
+                "traffic_source": (f"{rec['source']} @ {rec['commit']} (ncu dram read+write per launch)" if rec else None),
+                "dmma_pipe_active_pct_ncu": rec.get("dmma_pipe_pct") if rec else None,
+                "algorithmic_bytes_per_launch": (gm_batch * 2 + 1) * n * n * (16 if cfg.dtype.kind == "c" else 8),
                 "peak_source": "FP64 cuBLAS DGEMM 8192^3 via torch.matmul measured in this run (MEASURED_PEAKS.json "
                                "holds only bf16 and HBM figures; nominal B200 FP64 ~37-40 TFLOP/s)",
                 "launch_ms": gm_ms, "launch_batch": gm_batch, "flops_per_launch": gm_flops,
-                "step_tflops": cfg.flops_per_eval() * chains / (ms_total / args.steps * 1e-3) / 1e12,
-                "step_frac_of_peak": cfg.flops_per_eval() * chains / (ms_total / args.steps * 1e-3) / 1e12 / peak}
+                "step_tflops": step_tflops, "step_frac_of_peak": step_tflops / peak}
+        # second entry: the kernel furthest from its bound -- the LDR factorisation (pivoted QR + Q formation)
+        F = sla.ldr(torch.empty((chains, n, n), dtype=dt, device="cuda"))
+        if cfg.inverse == "IpA":
+            sla.greens_chain(expK_d, fields_d, cfg.lam, cfg.n_stab, "IpA", G=G, logdet=logdet, sign=sign, out_F=F, ws=ws)
+        else:   # the IpUV driver does not return its two factorisations: take the IpA chain's
+            sla.greens_chain(expK_d, fields_d, cfg.lam, cfg.n_stab, "IpA", G=G, logdet=logdet, sign=sign, out_F=F, ws=ws)
+        lm_ms, lm_flops, lm_algo, lm_launches = measure_ldr_kernel(torch, sla, cfg, F)
+        del F
+        lrec = ncu_record("ldr", cfg.name)
+        l_ach = lm_flops / (lm_ms * 1e-3) / 1e12
+        roof_ldr = {"bound": "tensor", "kernel": f"ldr! of the whole batch (LDR kernel family: {lm_algo}, {lm_launches} launch(es))",
+                    "achieved": l_ach, "peak": peak, "unit": "TFLOP/s", "frac": l_ach / peak,
+                    "traffic": lrec["dram_bytes_per_launch"] if lrec else None,
+                    "traffic_source": (f"{lrec['source']} @ {lrec['commit']}" if lrec else None),
+                    "launch_ms": lm_ms, "launch_batch": chains, "flops_per_launch": lm_flops,
+                    "note": "algorithmic work 8/3 N^3 per matrix (4/3 pivoted QR + 4/3 Q formation); latency-bound "
+                            "per-column dependency chain, see DESIGN.md section 4"}
         if world == 1 and not args.no_cpu:
+            # restore the results of the timed configuration for the parity check below
+            sla.greens_chain(expK_d, fields_d, cfg.lam, cfg.n_stab, cfg.inverse, G=G, logdet=logdet, sign=sign, ws=ws)
+            torch.cuda.synchronize()
             cpub, (Gr, lr, sr) = cpu_baseline(cfg)
             k = min(len(lr), chains)
             if k > 0 and not args.no_parity:   # chains 0..k-1 of this rank against the same chains of the CPU leg
                 Gg = sla.to_host(G[:k])
-                parity = {"chains_checked": k,
+                ld_g, sg_g = logdet.cpu().numpy(), sign.cpu().numpy()
+                parity = {"chains_checked": k, "ldr_kernel": ldr_algo,
                           "max_rel_err_G": float(max(np.max(np.abs(Gg[i] - Gr[i])) / np.max(np.abs(Gr[i])) for i in range(k))),
-                          "max_abs_err_logdet": float(np.max(np.abs(logdet_h.numpy()[:k] - lr[:k]))),
-                          "sign_mismatch": int(np.sum(np.abs(sign_h.numpy()[:k] - sr[:k]) > 1e-9))}
+                          "max_abs_err_logdet": float(np.max(np.abs(ld_g[:k] - lr[:k]))),
+                          "sign_mismatch": int(np.sum(np.abs(sg_g[:k] - sr[:k]) > 1e-9)),
+                          "e2e_host_copy_matches_device": bool(np.array_equal(np.swapaxes(G_h[:k].numpy(), 1, 2), Gg))}
     if rank == 0:
-        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-               "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "c128" if cfg.dtype.kind == "c" else "f64",
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+               "warmup": warm, "ms_per_step": ms_total / steps, "higher_is_better": True,
+               "scaling": args.scaling, "vs_baseline": None, "dtype": "c128" if cfg.dtype.kind == "c" else "f64",
                "data": "synthetic",
                "config": config_json(cfg, world, {"l2_policy": "working set per step (group products + state, "
-                                                  f"{ws.numel() / 2**30:.2f} GiB) is larger than the 126 MB L2"}),
+                                                  f"{ws.numel() / 2**30:.2f} GiB) is larger than the 126 MB L2"},
+                                     total_chains, args.scaling),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                       "ms_per_step": ms_e2e / args.steps},
-               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpub,
-               "parity": parity}
+                       "ms_per_step": ms_e2e / steps,
+                       "pipelining": "D2H of step k on a copy stream overlaps step k+1 (double-buffered outputs); the "
+                                     "clock stops after the last step's results are in host memory"},
+               "gpu_launches": int(launches), "ldr_kernel": ldr_algo, "clocks": clocks, "roofline": roof,
+               "roofline_ldr": roof_ldr, "cpu_baseline": cpub, "parity": parity}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -345,11 +467,14 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: per config, C2 = 20)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2")
-    ap.add_argument("--chains", type=int, default=None, help="chains per GPU (default: the config's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's per-GPU share on every rank; strong: the config's total split over the ranks")
+    ap.add_argument("--chains", type=int, default=None,
+                    help="chains per GPU (weak) or in total (strong); default: the config's")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()

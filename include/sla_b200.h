@@ -38,7 +38,18 @@ extern "C" {
 #define SLA_OP_C 1 /* conjugate transpose (adjoint) */
 #define SLA_INV_IPA 0
 #define SLA_INV_IPUV 1
-#define SLA_ENOTIMPL (-100)
+#define SLA_ENOTIMPL (-100) /* the requested (forced) kernel does not exist for this element type / size */
+#define SLA_EDEVICE (-101)  /* the handle was created on another device than the calling thread's current one */
+/* values of sla_last_ldr_algo(): which LDR factorisation kernel the dispatcher chose */
+#define SLA_LDR_ALGO_NONE 0
+#define SLA_LDR_ALGO_REG 1       /* register-resident cluster kernel (csrc/sla_ldr_reg.cu) */
+#define SLA_LDR_ALGO_CLUSTER 2   /* shared-memory cluster kernel (csrc/sla_ldr_cluster.cu) */
+#define SLA_LDR_ALGO_STREAMING 3 /* one CTA per matrix, L2-streaming (csrc/sla_ldr.cu) */
+#define SLA_LDR_ALGO_HYBRID 4    /* registers + shared memory, clusters of 2 (csrc/sla_ldr_reg.cu) */
+#define SLA_LDR_ALGO_BLOCKED 5   /* blocked panel + tensor-core trailing update (csrc/sla_ldr_blk.cu) */
+/* per-matrix info codes (sla_workspace_info): k > 0 = U(k,k) exactly zero or not finite in an LU (src/lu.jl:75,91);
+ * SLA_INFO_RANGE = a column norm of an ldr! input left the range in which squared norms are representable */
+#define SLA_INFO_RANGE (-1)
 
 #if defined(__GNUC__)
 #define SLA_API __attribute__((visibility("default")))
@@ -58,6 +69,14 @@ SLA_API void sla_debug_set_ldr_prof(void* dev_buffer_128_int64);
 SLA_API int sla_create(sla_handle_t* handle, void* stream);
 SLA_API int sla_destroy(sla_handle_t handle);
 SLA_API int sla_set_stream(sla_handle_t handle, void* stream);
+/* diagnostics for the tests: SLA_LDR_ALGO_* of the last factorisation launched through this handle, and how many
+ * factorisations each algorithm has served on it */
+SLA_API int sla_last_ldr_algo(sla_handle_t handle);
+SLA_API unsigned long long sla_ldr_algo_launches(sla_handle_t handle, int algo);
+
+/* largest supported matrix size for an element type (the QR / LU panels of one matrix must fit one SM's shared
+ * memory); larger n: sla_workspace_bytes() returns 0 and every entry point returns SLA_ENOTIMPL */
+SLA_API int sla_max_n(int dtype);
 
 /* LDRWorkspace equivalent (src/LDR.jl:51-70, ldr_workspace src/LDR.jl:267-282): bytes of the scratch
  * blob every call below takes as `ws` (M, M', M'', the LU/QR scratch, v and the per-matrix scalars). */
@@ -163,6 +182,11 @@ SLA_API int sla_gemm(sla_handle_t h, int dtype, int opa, int opb, int m, int n, 
  *   Lout/dout/Rout: optional (may be NULL) final LDR factorisation F (SLA_INV_IPA only)
  *   ws     : blob of at least sla_greens_chain_workspace_bytes(...) bytes */
 SLA_API size_t sla_greens_chain_workspace_bytes(int dtype, int n, int batch, int L, int n_stab);
+/* local part of the cross-walker reduction: out4 = [sum logdet, sum Re sign, sum Im sign, batch] on
+ * the device, in a fixed summation order; the caller hands out4 straight to ncclAllReduce(sum) */
+SLA_API int sla_walker_sums(sla_handle_t h, int dtype, int batch, const double* logdet, const void* sign, double* out4);
+/* device pointer to the per-chain info codes (int[batch]) inside a sla_greens_chain workspace blob */
+SLA_API int* sla_greens_chain_workspace_info(void* ws, int dtype, int n, int batch, int L, int n_stab);
 SLA_API int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L, int n_stab, const void* expK,
                      const signed char* fields, double lam, int inverse, void* G, double* logdet, void* sign,
                      void* Lout, double* dout, void* Rout, void* ws, size_t ws_bytes);

@@ -21,6 +21,8 @@ def load():
         _lib.oracle_eval_batch.restype = C.c_int
         _lib.oracle_eval_batch.argtypes = [C.c_int, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_void_p,
                                            C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.oracle_eval_batch_bt.restype = C.c_int
+        _lib.oracle_eval_batch_bt.argtypes = _lib.oracle_eval_batch.argtypes + [C.c_int]
         _lib.oracle_blas_config.restype = C.c_char_p
     return _lib
 
@@ -29,9 +31,9 @@ def blas_config() -> str:
     return load().oracle_blas_config().decode()
 
 
-def eval_batch(expK, fields, lam, n_stab, inverse="IpA", nthreads=1):
+def eval_batch(expK, fields, lam, n_stab, inverse="IpA", nthreads=1, blas_threads=1):
     """fields int8 (chains, L, n) -> (G (chains,n,n) ordinary indexing, logdet, sign); one chain per
-    worker thread, 1 BLAS thread each."""
+    worker thread, `blas_threads` BLAS threads each (default 1)."""
     lib = load()
     chains, L, n = fields.shape
     cplx = np.iscomplexobj(expK)
@@ -41,8 +43,8 @@ def eval_batch(expK, fields, lam, n_stab, inverse="IpA", nthreads=1):
     G = np.zeros((chains, n, n), dtype=dt)          # each [c] is filled column-major -> transpose below
     logdet = np.zeros(chains)
     sgn = np.zeros(chains, dtype=dt)
-    rc = lib.oracle_eval_batch(int(cplx), n, L, n_stab, chains, eK.ctypes.data, f.ctypes.data, float(lam),
-                               0 if inverse == "IpA" else 1, G.ctypes.data, logdet.ctypes.data, sgn.ctypes.data,
-                               int(nthreads))
+    rc = lib.oracle_eval_batch_bt(int(cplx), n, L, n_stab, chains, eK.ctypes.data, f.ctypes.data, float(lam),
+                                  0 if inverse == "IpA" else 1, G.ctypes.data, logdet.ctypes.data, sgn.ctypes.data,
+                                  int(nthreads), int(blas_threads))
     assert rc == 0
     return np.swapaxes(G, 1, 2).copy(), logdet, sgn

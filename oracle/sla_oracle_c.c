@@ -232,13 +232,14 @@ static void* worker(void* arg) {
 }
 
 /* dtype 0 = Float64, 1 = ComplexF64; inverse 0 = inv_IpA!, 1 = inv_IpUV!; column-major matrices;
- * fields int8 [chains][L][n]; nthreads worker threads x 1 BLAS thread each. */
-int oracle_eval_batch(int dtype, long n, long L, long n_stab, long chains, const void* expK,
-                      const signed char* fields, double lam, int inverse, void* G, double* logdet, void* sgn,
-                      int nthreads) {
+ * fields int8 [chains][L][n]; nthreads worker threads x blas_threads BLAS threads each (the fair DQMC arrangement is
+ * one chain per core x 1 BLAS thread; 1 worker x nproc BLAS threads is reported beside it for transparency). */
+int oracle_eval_batch_bt(int dtype, long n, long L, long n_stab, long chains, const void* expK,
+                         const signed char* fields, double lam, int inverse, void* G, double* logdet, void* sgn,
+                         int nthreads, int blas_threads) {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > chains) nthreads = (int)chains;
-    scipy_openblas_set_num_threads64_(1);
+    scipy_openblas_set_num_threads64_(blas_threads < 1 ? 1 : blas_threads);
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
     job_t* jobs = (job_t*)malloc(sizeof(job_t) * nthreads);
     for (int t = 0; t < nthreads; ++t) {
@@ -250,6 +251,12 @@ int oracle_eval_batch(int dtype, long n, long L, long n_stab, long chains, const
     free(th);
     free(jobs);
     return 0;
+}
+
+int oracle_eval_batch(int dtype, long n, long L, long n_stab, long chains, const void* expK,
+                      const signed char* fields, double lam, int inverse, void* G, double* logdet, void* sgn,
+                      int nthreads) {
+    return oracle_eval_batch_bt(dtype, n, L, n_stab, chains, expK, fields, lam, inverse, G, logdet, sgn, nthreads, 1);
 }
 
 const char* oracle_blas_config(void) { return scipy_openblas_get_config64_(); }

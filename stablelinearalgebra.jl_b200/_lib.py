@@ -15,6 +15,9 @@ LIB_PATH = os.environ.get("SLA_B200_LIB") or os.path.join(HERE, "csrc", "libsla_
 SLA_F64, SLA_C64 = 0, 1
 SLA_OP_N, SLA_OP_C = 0, 1
 SLA_INV_IPA, SLA_INV_IPUV = 0, 1
+SLA_ENOTIMPL, SLA_EDEVICE = -100, -101
+SLA_INFO_RANGE = -1
+LDR_ALGOS = {0: "none", 1: "reg", 2: "cluster", 3: "streaming", 4: "hybrid", 5: "blocked"}
 
 _vp, _i, _ll, _sz, _dbl = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_double
 _common = [_vp, _i, _i, _i]  # handle, dtype, n, batch
@@ -26,6 +29,10 @@ SIGNATURES = {
     "sla_create": (_i, [C.POINTER(_vp), _vp]),
     "sla_destroy": (_i, [_vp]),
     "sla_set_stream": (_i, [_vp, _vp]),
+    "sla_last_ldr_algo": (_i, [_vp]),
+    "sla_ldr_algo_launches": (C.c_ulonglong, [_vp, _i]),
+    "sla_greens_chain_workspace_info": (_vp, [_vp, _i, _i, _i, _i, _i]),
+    "sla_max_n": (_i, [_i]),
     "sla_workspace_bytes": (_sz, [_i, _i, _i]),
     "sla_workspace_info": (_vp, [_vp, _i, _i, _i]),
     "sla_ldr": (_i, _common + [_vp, _vp, _vp, _vp]),
@@ -55,6 +62,7 @@ SIGNATURES = {
     "sla_inv_UpV": (_i, _common + [_vp] * 10),
     "sla_inv_invUpV": (_i, _common + [_vp] * 10),
     "sla_gemm": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _ll, _vp, _i, _ll, _vp, _i, _ll, _i, _i]),
+    "sla_walker_sums": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "sla_greens_chain_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sla_greens_chain": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _dbl, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
 }

@@ -25,7 +25,7 @@ __all__ = [
     "copyto_", "adjoint_", "lmul_", "rmul_", "mul_", "logabsdet", "det_lu_", "inv_lu_",
     "ldiv_", "rdiv_", "ldiv_lu_",
     "inv_IpA_", "inv_IpUV_", "inv_UpV_", "inv_invUpV_", "gemm", "greens_chain", "check_info",
-    "greens_chain_workspace_bytes", "SlaError",
+    "greens_chain_workspace_bytes", "greens_chain_info", "last_ldr_algo", "ldr_algo_launches", "walker_sums", "SlaError",
 ]
 
 
@@ -44,8 +44,12 @@ def _dtype_code(t: torch.Tensor) -> int:
 def _check(code: int, what: str):
     if code == 0:
         return
+    if code == _lib.SLA_ENOTIMPL:
+        raise SlaError(f"{what}: the requested kernel does not exist for this element type / size (SLA_ENOTIMPL)")
+    if code == _lib.SLA_EDEVICE:
+        raise SlaError(f"{what}: the handle belongs to another device than the current one (SLA_EDEVICE)")
     if code < 0:
-        raise SlaError(f"{what}: invalid argument #{-code}" if code != -100 else f"{what}: not implemented")
+        raise SlaError(f"{what}: invalid argument #{-code}")
     raise SlaError(f"{what}: CUDA error {code - 1000}")
 
 
@@ -127,6 +131,9 @@ class LDRWorkspace:
         self.n, self.batch, self.dtype = n, batch, dtype
         self.code = _lib.SLA_F64 if dtype == torch.float64 else _lib.SLA_C64
         self.nbytes = lib.sla_workspace_bytes(self.code, n, batch)
+        if self.nbytes == 0:
+            raise SlaError(f"unsupported size n={n} (1 <= n <= {lib.sla_max_n(self.code)} for this element type) or "
+                           f"batch={batch}")
         self.blob = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
 
     def info(self) -> torch.Tensor:
@@ -137,12 +144,41 @@ class LDRWorkspace:
         return self.blob[off:off + 4 * self.batch].view(torch.int32)
 
 
-def check_info(ws: LDRWorkspace):
-    """Lazy ``chklapackerror`` (src/lu.jl:75,91): raise if any matrix hit an exactly-zero pivot."""
-    info = ws.info().cpu().numpy()
+def _raise_info(info):
     bad = np.nonzero(info)[0]
     if bad.size:
-        raise np.linalg.LinAlgError(f"singular U({info[bad[0]]},{info[bad[0]]}) in batch entry {bad[0]}")
+        k = int(info[bad[0]])
+        if k == _lib.SLA_INFO_RANGE:
+            raise np.linalg.LinAlgError(f"ldr!: a column norm of batch entry {bad[0]} is outside the range in which "
+                                        "squared norms are representable (about 1e-145 .. 1e150)")
+        raise np.linalg.LinAlgError(f"singular U({k},{k}) in batch entry {bad[0]}")
+
+
+def check_info(ws: LDRWorkspace):
+    """Lazy ``chklapackerror`` (src/lu.jl:75,91): raise if any matrix hit an exactly-zero (or non-finite) pivot in ANY
+    of the LU factorisations of the last call on this workspace, or if ``ldr!`` met a column norm out of range."""
+    _raise_info(ws.info().cpu().numpy())
+
+
+def greens_chain_info(ws: torch.Tensor, dtype: torch.dtype, n: int, batch: int, L: int, n_stab: int) -> torch.Tensor:
+    """The per-chain info codes inside a ``greens_chain`` workspace blob (same meaning as ``LDRWorkspace.info``)."""
+    lib = _lib.load()
+    code = _lib.SLA_F64 if dtype == torch.float64 else _lib.SLA_C64
+    p = lib.sla_greens_chain_workspace_info(C.c_void_p(ws.data_ptr()), code, n, batch, L, n_stab)
+    off = p - ws.data_ptr()
+    return ws[off:off + 4 * batch].view(torch.int32)
+
+
+def last_ldr_algo() -> str:
+    """Name of the LDR factorisation kernel the dispatcher used for the last ``ldr!`` on the current (device, stream)
+    handle: one of ``_lib.LDR_ALGOS`` (diagnostics; the parity tests assert which kernel they exercised)."""
+    lib, h = _Handle.current()
+    return _lib.LDR_ALGOS[lib.sla_last_ldr_algo(h)]
+
+
+def ldr_algo_launches() -> dict:
+    lib, h = _Handle.current()
+    return {name: int(lib.sla_ldr_algo_launches(h, code)) for code, name in _lib.LDR_ALGOS.items() if code}
 
 
 def ldr_workspace(A) -> LDRWorkspace:
@@ -152,9 +188,31 @@ def ldr_workspace(A) -> LDRWorkspace:
 
 
 def _chk_ws(ws: LDRWorkspace, F):
+    if not isinstance(ws, LDRWorkspace):
+        raise SlaError("an LDRWorkspace is required (ldr_workspace(A))")
     L = F.L if isinstance(F, LDR) else F
     if ws.n != L.shape[1] or ws.batch != L.shape[0] or ws.dtype != L.dtype:
         raise SlaError("workspace does not match (n, batch, eltype)")
+    if ws.blob.device != L.device:
+        raise SlaError("workspace lives on another device")
+
+
+def _chk_mat(M, F, what, shared_ok=True):
+    """A matrix operand of an LDR call: same (n, n), eltype and device; batch equal to F's (or 1 = shared)."""
+    L = F.L if isinstance(F, LDR) else F
+    if M.ndim != 3 or M.shape[1:] != L.shape[1:]:
+        raise SlaError(f"{what}: expected a column-major batch of {L.shape[1]}x{L.shape[2]} matrices, got {tuple(M.shape)}")
+    if M.dtype != L.dtype:
+        raise SlaError(f"{what}: element type {M.dtype} does not match {L.dtype}")
+    if M.device != L.device:
+        raise SlaError(f"{what}: operand lives on another device")
+    if M.shape[0] != L.shape[0] and not (shared_ok and M.shape[0] == 1):
+        raise SlaError(f"{what}: batch {M.shape[0]} does not match {L.shape[0]}" + (" (or 1 = shared)" if shared_ok else ""))
+
+
+def _chk_ldr(U: LDR, V: LDR, what):
+    if U.L.shape != V.L.shape or U.dtype != V.dtype or U.L.device != V.L.device:
+        raise SlaError(f"{what}: the two factorisations differ in (n, batch), element type or device")
 
 
 def _identity_(F: LDR):
@@ -190,6 +248,8 @@ def ldr_(F: LDR, A=None, ws: LDRWorkspace | None = None):
                "sla_copy")
         return None
     _chk_ws(ws, F)
+    if A is not None:
+        _chk_mat(A, F, "ldr!(F, A, ws)")
     if A is None:
         _check(lib.sla_ldr(h, code, F.n, F.batch, _ptr(F.L), _ptr(F.d), _ptr(F.R), _ptr(ws.blob)), "sla_ldr")
     else:
@@ -226,6 +286,7 @@ def copyto_(U, V, ws: LDRWorkspace | None = None):
         return ldr_(U, V, ws)
     lib, h = _Handle.current()
     _chk_ws(ws, V)
+    _chk_mat(U, V, "copyto!(U, V::LDR, ws)", shared_ok=False)
     _check(lib.sla_ldr_to_mat(h, _dtype_code(U), V.n, V.batch, _ptr(U), _ptr(V.L), _ptr(V.d), _ptr(V.R),
                               _ptr(ws.blob)), "sla_ldr_to_mat")
 
@@ -234,6 +295,7 @@ def adjoint_(At, A: LDR, ws: LDRWorkspace):
     """``adjoint!(A', A::LDR, ws)`` (overloaded_functions.jl:75-86)."""
     lib, h = _Handle.current()
     _chk_ws(ws, A)
+    _chk_mat(At, A, "adjoint!", shared_ok=False)
     _check(lib.sla_adjoint(h, _dtype_code(At), A.n, A.batch, _ptr(At), _ptr(A.L), _ptr(A.d), _ptr(A.R),
                            _ptr(ws.blob)), "sla_adjoint")
 
@@ -248,13 +310,16 @@ def lmul_(U, V, ws: LDRWorkspace):
     lib, h = _Handle.current()
     if isinstance(U, LDR) and not isinstance(V, LDR):
         _chk_ws(ws, U)
+        _chk_mat(V, U, "lmul!(U::LDR, V)", shared_ok=False)
         return _check(lib.sla_lmul_ldr_mat(h, _dtype_code(V), U.n, U.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V),
                                            _ptr(ws.blob)), "sla_lmul_ldr_mat")
     _chk_ws(ws, V)
     code = _dtype_code(V.L)
     if not isinstance(U, LDR):
+        _chk_mat(U, V, "lmul!(U, V::LDR)")
         return _check(lib.sla_lmul_mat_ldr(h, code, V.n, V.batch, _ptr(U), _mat_stride(U, V), _ptr(V.L), _ptr(V.d),
                                            _ptr(V.R), _ptr(ws.blob)), "sla_lmul_mat_ldr")
+    _chk_ldr(U, V, "lmul!(U::LDR, V::LDR)")
     return _check(lib.sla_lmul_ldr_ldr(h, code, V.n, V.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V.L), _ptr(V.d),
                                        _ptr(V.R), _ptr(ws.blob)), "sla_lmul_ldr_ldr")
 
@@ -265,13 +330,16 @@ def rmul_(U, V, ws: LDRWorkspace):
     lib, h = _Handle.current()
     if not isinstance(U, LDR):
         _chk_ws(ws, V)
+        _chk_mat(U, V, "rmul!(U, V::LDR)", shared_ok=False)
         return _check(lib.sla_rmul_mat_ldr(h, _dtype_code(U), V.n, V.batch, _ptr(U), _ptr(V.L), _ptr(V.d), _ptr(V.R),
                                            _ptr(ws.blob)), "sla_rmul_mat_ldr")
     _chk_ws(ws, U)
     code = _dtype_code(U.L)
     if not isinstance(V, LDR):
+        _chk_mat(V, U, "rmul!(U::LDR, V)")
         return _check(lib.sla_rmul_ldr_mat(h, code, U.n, U.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V),
                                            _mat_stride(V, U), _ptr(ws.blob)), "sla_rmul_ldr_mat")
+    _chk_ldr(U, V, "rmul!(U::LDR, V::LDR)")
     return _check(lib.sla_rmul_ldr_ldr(h, code, U.n, U.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V.L), _ptr(V.d),
                                        _ptr(V.R), _ptr(ws.blob)), "sla_rmul_ldr_ldr")
 
@@ -306,13 +374,16 @@ def ldiv_(*args):
     lib, h = _Handle.current()
     if isinstance(U, LDR) and not isinstance(V, LDR):
         _chk_ws(ws, U)
+        _chk_mat(V, U, "ldiv!(U::LDR, V)", shared_ok=False)
         return _check(lib.sla_ldiv_ldr_mat(h, _dtype_code(V), U.n, U.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V),
                                            _ptr(ws.blob)), "sla_ldiv_ldr_mat")
     _chk_ws(ws, V)
     code = _dtype_code(V.L)
     if isinstance(U, LDR):
+        _chk_ldr(U, V, "ldiv!(U::LDR, V::LDR)")
         return _check(lib.sla_ldiv_ldr_ldr(h, code, V.n, V.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V.L), _ptr(V.d),
                                            _ptr(V.R), _ptr(ws.blob)), "sla_ldiv_ldr_ldr")
+    _chk_mat(U, V, "ldiv!(U, V::LDR)")
     return _check(lib.sla_ldiv_mat_ldr(h, code, V.n, V.batch, _ptr(U), _mat_stride(U, V), _ptr(V.L), _ptr(V.d), _ptr(V.R),
                                        _ptr(ws.blob)), "sla_ldiv_mat_ldr")
 
@@ -332,13 +403,16 @@ def rdiv_(*args):
     lib, h = _Handle.current()
     if not isinstance(U, LDR):
         _chk_ws(ws, V)
+        _chk_mat(U, V, "rdiv!(U, V::LDR)", shared_ok=False)
         return _check(lib.sla_rdiv_mat_ldr(h, _dtype_code(U), V.n, V.batch, _ptr(U), _ptr(V.L), _ptr(V.d), _ptr(V.R),
                                            _ptr(ws.blob)), "sla_rdiv_mat_ldr")
     _chk_ws(ws, U)
     code = _dtype_code(U.L)
     if isinstance(V, LDR):
+        _chk_ldr(U, V, "rdiv!(U::LDR, V::LDR)")
         return _check(lib.sla_rdiv_ldr_ldr(h, code, U.n, U.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V.L), _ptr(V.d),
                                            _ptr(V.R), _ptr(ws.blob)), "sla_rdiv_ldr_ldr")
+    _chk_mat(V, U, "rdiv!(U::LDR, V)")
     return _check(lib.sla_rdiv_ldr_mat(h, code, U.n, U.batch, _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V), _mat_stride(V, U),
                                        _ptr(ws.blob)), "sla_rdiv_ldr_mat")
 
@@ -372,6 +446,7 @@ def ldiv_lu_(A, B, ws: LDRWorkspace):
     """``ldiv_lu!(A, B, ws)`` (src/lu.jl:167-176): B := A^-1 B, A := LU; returns (log|det A^-1|, sign det A^-1)."""
     lib, h = _Handle.current()
     _chk_ws(ws, A)
+    _chk_mat(B, A, "ldiv_lu!(A, B, ws)", shared_ok=False)
     logdet, sgn = _scalars(A, A.shape[0], A.device)
     _check(lib.sla_ldiv_lu(h, _dtype_code(A), A.shape[1], A.shape[0], _ptr(A), _ptr(B), _ptr(logdet), _ptr(sgn),
                            _ptr(ws.blob)), "sla_ldiv_lu")
@@ -392,6 +467,7 @@ def inv_IpA_(G, A: LDR, ws: LDRWorkspace):
     """``inv_IpA!(G, A, ws)`` (exported_functions.jl:25-71): G := (I + A)^-1 -> (log|det G|, sign)."""
     lib, h = _Handle.current()
     _chk_ws(ws, A)
+    _chk_mat(G, A, "inv_IpA!(G, A, ws)", shared_ok=False)
     logdet, sgn = _scalars(A, A.batch, A.L.device)
     _check(lib.sla_inv_IpA(h, _dtype_code(G), A.n, A.batch, _ptr(G), _ptr(A.L), _ptr(A.d), _ptr(A.R), _ptr(logdet),
                            _ptr(sgn), _ptr(ws.blob)), "sla_inv_IpA")
@@ -402,6 +478,8 @@ def _uv(name, G, U: LDR, V: LDR, ws: LDRWorkspace):
     lib, h = _Handle.current()
     _chk_ws(ws, U)
     _chk_ws(ws, V)
+    _chk_ldr(U, V, name)
+    _chk_mat(G, U, name, shared_ok=False)
     logdet, sgn = _scalars(U, U.batch, U.L.device)
     fn = getattr(lib, name)
     _check(fn(h, _dtype_code(G), U.n, U.batch, _ptr(G), _ptr(U.L), _ptr(U.d), _ptr(U.R), _ptr(V.L), _ptr(V.d),
@@ -433,6 +511,17 @@ def gemm(C_, A, B, opa="N", opb="N", accumulate=False):
     ops = {"N": _lib.SLA_OP_N, "C": _lib.SLA_OP_C}
     _check(lib.sla_gemm(h, _dtype_code(C_), ops[opa], ops[opb], n, n, n, _ptr(A), n, sA, _ptr(B), n, sB, _ptr(C_), n,
                         n * n, batch, int(bool(accumulate))), "sla_gemm")
+
+
+def walker_sums(logdet: torch.Tensor, sign: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """``[sum logdet, sum Re sign, sum Im sign, batch]`` on the device (one kernel, fixed summation order): the local
+    part of the cross-walker all-reduce of SURVEY.md section 8(e)."""
+    lib, h = _Handle.current()
+    if out is None:
+        out = torch.empty(4, dtype=torch.float64, device=logdet.device)
+    _check(lib.sla_walker_sums(h, _dtype_code(sign), logdet.numel(), _ptr(logdet), _ptr(sign), _ptr(out)),
+           "sla_walker_sums")
+    return out
 
 
 def greens_chain_workspace_bytes(dtype: torch.dtype, n: int, batch: int, L: int, n_stab: int) -> int:

@@ -15,6 +15,9 @@ static long long* g_ldr_prof = nullptr;   // diagnostics only (sla_debug_set_ldr
 
 struct sla_handle_s {
     cudaStream_t stream;
+    int device = 0;           // the device the handle was created on (sla_create); every call checks it is current
+    int last_ldr_algo = 0;    // SLA_LDR_ALGO_* of the most recent LDR factorisation launched through this handle
+    unsigned long long ldr_algo_launches[8] = {};   // factorisations launched per algorithm
     // fused driver only: a lower-priority side stream on which the group products (independent of the chain
     // state) are built while the chain's latency-bound LDR kernels leave SMs idle; created lazily
     cudaStream_t side = nullptr;
@@ -76,11 +79,12 @@ template <typename T> struct Ws {
 };
 
 template <typename T> struct Ctx {
+    sla_handle_t h;
     cudaStream_t s;
     int n, batch;
     long long nn;  // n*n
     Ws<T> w;
-    Ctx(sla_handle_t h, int n_, int batch_, void* ws) : s(h->stream), n(n_), batch(batch_), nn((long long)n_ * n_), w(ws, n_, batch_) {}
+    Ctx(sla_handle_t h_, int n_, int batch_, void* ws) : h(h_), s(h_->stream), n(n_), batch(batch_), nn((long long)n_ * n_), w(ws, n_, batch_) {}
 
     int copy(T* dst, const T* src) const {
         if (dst == src) return 0;
@@ -156,10 +160,25 @@ template <typename T> struct Ctx {
             ldr_n256_resident(&c_reg, &c_hyb);
             if (c_reg > 0 && c_hyb > 0) hyb_pays = 100 * waves(batch, c_hyb) < 79 * waves(batch, c_reg);
         }
-        if (cs_hyb > 0 && (forced == 4 || hyb_pays)) CK(ldr_hyb_batched<T>(a, s));
-        else if (forced == 1 ? cs_reg > 0 : (forced == 0 && reg_pays)) CK(ldr_reg_batched<T>(a, s));
-        else if (forced == 2 ? cs_cl > 0 : (forced == 0 && cl_pays && cs_reg == 0)) CK(ldr_cluster_batched<T>(a, s));
-        else CK(ldr_batched<T>(a, s));
+        // a forced algorithm that does not apply to (T, n) is an error, never a silent fall-through to another kernel
+        int algo;
+        if (forced == 4) { if (cs_hyb == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_HYBRID; }
+        else if (forced == 1) { if (cs_reg == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_REG; }
+        else if (forced == 2) { if (cs_cl == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_CLUSTER; }
+        else if (forced == 3) algo = SLA_LDR_ALGO_STREAMING;
+        else if (hyb_pays) algo = SLA_LDR_ALGO_HYBRID;
+        else if (reg_pays) algo = SLA_LDR_ALGO_REG;
+        else if (cl_pays && cs_reg == 0) algo = SLA_LDR_ALGO_CLUSTER;
+        else algo = SLA_LDR_ALGO_STREAMING;
+        a.info = w.info;
+        switch (algo) {
+            case SLA_LDR_ALGO_HYBRID: CK(ldr_hyb_batched<T>(a, s)); break;
+            case SLA_LDR_ALGO_REG: CK(ldr_reg_batched<T>(a, s)); break;
+            case SLA_LDR_ALGO_CLUSTER: CK(ldr_cluster_batched<T>(a, s)); break;
+            default: CK(ldr_batched<T>(a, s)); break;
+        }
+        h->last_ldr_algo = algo;
+        ++h->ldr_algo_launches[algo];
         return 0;
     }
     // LU of A (destroyed).  invert: A^-1 -> X (and back into A if copy_back)
@@ -572,6 +591,7 @@ int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const
     const long long nn = c.nn;
     cudaStream_t s = c.s;
 
+    CK(cudaMemsetAsync(c.w.info, 0, (size_t)batch * sizeof(int), s));
     CK(hs_exp_batched(cw.ev, fields, lam, (long long)batch * L * n, s));
 
     // two LDR states: F (IpA), or V (first half of the groups) and U (second half) for IpUV
@@ -669,11 +689,32 @@ int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const
 #define CHECK_COMMON(h, dtype, n, batch)                 \
     do {                                                 \
         if (!(h)) return -1;                             \
+        if (!device_is_current(h)) return SLA_EDEVICE;   \
         if ((dtype) != SLA_F64 && (dtype) != SLA_C64) return -2; \
         if ((n) <= 0) return -3;                         \
+        if (!n_supported(dtype, n)) return SLA_ENOTIMPL;  \
         if ((batch) < 0) return -4;                      \
         if ((batch) == 0) return 0;                      \
     } while (0)
+
+// largest n: the QR / LU panels of one matrix must fit the shared memory of one CTA (sla_max_n)
+static inline bool n_supported(int dtype, int n) {
+    return dtype == SLA_F64 ? (ldr_twork_elems<double>(n) > 0 && lu_supported<double>(n))
+                            : (ldr_twork_elems<cplx>(n) > 0 && lu_supported<cplx>(n));
+}
+// the handle's device must be the calling thread's current device (buffers, streams and kernel attributes are per device)
+static inline bool device_is_current(sla_handle_t h) {
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess && dev == h->device;
+}
+// LAPACK-style info codes accumulate over the kernels of ONE entry point: cleared here, on the stream, and only
+// ever raised from 0 by the kernels (the first failure is the one reported, as chklapackerror would throw it)
+static inline int clear_info(sla_handle_t h, int dtype, int n, int batch, void* ws) {
+    int* info = dtype == SLA_F64 ? Ws<double>(ws, n, batch).info : Ws<cplx>(ws, n, batch).info;
+    cudaError_t e = cudaMemsetAsync(info, 0, (size_t)batch * sizeof(int), h->stream);
+    return e == cudaSuccess ? 0 : 1000 + (int)e;
+}
+#define CLEAR_INFO(h, dtype, n, batch, ws) do { int r__ = clear_info(h, dtype, n, batch, ws); if (r__) return r__; } while (0)
 
 #define DISPATCH(dtype, fn, ...) \
     ((dtype) == SLA_F64 ? fn<double>(__VA_ARGS__) : fn<cplx>(__VA_ARGS__))
@@ -682,7 +723,7 @@ extern "C" {
 
 int sla_version(void) { return 100; }
 
-unsigned long long sla_launch_count(void) { return g_launch_count; }
+unsigned long long sla_launch_count(void) { return g_launch_count.load(); }
 
 void sla_debug_set_ldr_prof(void* dev_buffer_128_int64) { g_ldr_prof = static_cast<long long*>(dev_buffer_128_int64); }
 
@@ -693,6 +734,7 @@ int sla_create(sla_handle_t* handle, void* stream) {
     sla_handle_s* h = new (std::nothrow) sla_handle_s;
     if (!h) return -1;
     h->stream = static_cast<cudaStream_t>(stream);
+    h->device = dev;
     *handle = h;
     return 0;
 }
@@ -707,14 +749,27 @@ int sla_destroy(sla_handle_t handle) {
     return 0;
 }
 
+int sla_last_ldr_algo(sla_handle_t handle) { return handle ? handle->last_ldr_algo : -1; }
+
+unsigned long long sla_ldr_algo_launches(sla_handle_t handle, int algo) {
+    return (handle && algo >= 0 && algo < 8) ? handle->ldr_algo_launches[algo] : 0ull;
+}
+
 int sla_set_stream(sla_handle_t handle, void* stream) {
     if (!handle) return -1;
     handle->stream = static_cast<cudaStream_t>(stream);
     return 0;
 }
 
+int sla_max_n(int dtype) {
+    if (dtype != SLA_F64 && dtype != SLA_C64) return 0;
+    int lo = 1, hi = 1 << 14;   // n_supported is monotone in n
+    while (lo < hi) { int mid = (lo + hi + 1) / 2; if (n_supported(dtype, mid)) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
 size_t sla_workspace_bytes(int dtype, int n, int batch) {
-    if (n <= 0 || batch <= 0) return 0;
+    if (n <= 0 || batch <= 0 || (dtype != SLA_F64 && dtype != SLA_C64) || !n_supported(dtype, n)) return 0;
     return dtype == SLA_F64 ? Ws<double>::bytes(n, batch) : Ws<cplx>::bytes(n, batch);
 }
 
@@ -728,7 +783,7 @@ int* sla_workspace_info(void* ws, int dtype, int n, int batch) {
 
 int sla_ldr(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!ws) return -8;
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!ws) return -8; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldr_impl<double>(h, n, batch, (double*)L, d, (double*)R, ws);
     return ldr_impl<cplx>(h, n, batch, (cplx*)L, d, (cplx*)R, ws);
 }
@@ -736,7 +791,7 @@ int sla_ldr(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, voi
 int sla_ldr_from(sla_handle_t h, int dtype, int n, int batch, const void* A, long long strideA, void* L, double* d,
                  void* R, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!A) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10;
+    if (!A) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldr_from_impl<double>(h, n, batch, (const double*)A, strideA, (double*)L, d, (double*)R, ws);
     return ldr_from_impl<cplx>(h, n, batch, (const cplx*)A, strideA, (cplx*)L, d, (cplx*)R, ws);
 }
@@ -763,7 +818,7 @@ int sla_copy(sla_handle_t h, int dtype, int n, int batch, void* Lo, double* dout
 int sla_ldr_to_mat(sla_handle_t h, int dtype, int n, int batch, void* A, const void* L, const double* d,
                    const void* R, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!A) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9;
+    if (!A) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldr_to_mat_impl<double>(h, n, batch, (double*)A, (const double*)L, d, (const double*)R, ws);
     return ldr_to_mat_impl<cplx>(h, n, batch, (cplx*)A, (const cplx*)L, d, (const cplx*)R, ws);
 }
@@ -771,7 +826,7 @@ int sla_ldr_to_mat(sla_handle_t h, int dtype, int n, int batch, void* A, const v
 int sla_adjoint(sla_handle_t h, int dtype, int n, int batch, void* At, const void* L, const double* d, const void* R,
                 void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!At) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9;
+    if (!At) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return adjoint_impl<double>(h, n, batch, (double*)At, (const double*)L, d, (const double*)R, ws);
     return adjoint_impl<cplx>(h, n, batch, (cplx*)At, (const cplx*)L, d, (const cplx*)R, ws);
 }
@@ -779,7 +834,7 @@ int sla_adjoint(sla_handle_t h, int dtype, int n, int batch, void* At, const voi
 int sla_lmul_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U, long long strideU, void* L,
                      double* d, void* R, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!U) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10;
+    if (!U) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return lmul_mat_ldr_impl<double>(h, n, batch, (const double*)U, strideU, (double*)L, d, (double*)R, ws);
     return lmul_mat_ldr_impl<cplx>(h, n, batch, (const cplx*)U, strideU, (cplx*)L, d, (cplx*)R, ws);
 }
@@ -787,7 +842,7 @@ int sla_lmul_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U,
 int sla_rmul_ldr_mat(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R, const void* V,
                      long long strideV, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -10;
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return rmul_ldr_mat_impl<double>(h, n, batch, (double*)L, d, (double*)R, (const double*)V, strideV, ws);
     return rmul_ldr_mat_impl<cplx>(h, n, batch, (cplx*)L, d, (cplx*)R, (const cplx*)V, strideV, ws);
 }
@@ -800,7 +855,7 @@ int sla_lmul_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, const void* UL
                      void* VL, double* Vd, void* VR, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
     UV_NULLCHECK();
-    if (!ws) return -11;
+    if (!ws) return -11; CLEAR_INFO(h, dtype, n, batch, ws);
     if (UL == VL || UR == VR || Ud == Vd) return -8;  // U and V must be distinct (overloaded_functions.jl:179,185)
     if (dtype == SLA_F64)
         return lmul_ldr_ldr_impl<double>(h, n, batch, (const double*)UL, Ud, (const double*)UR, (double*)VL, Vd, (double*)VR, ws);
@@ -811,7 +866,7 @@ int sla_rmul_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, doub
                      const double* Vd, const void* VR, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
     UV_NULLCHECK();
-    if (!ws) return -11;
+    if (!ws) return -11; CLEAR_INFO(h, dtype, n, batch, ws);
     if (UL == VL || UR == VR || Ud == Vd) return -8;
     if (dtype == SLA_F64)
         return rmul_ldr_ldr_impl<double>(h, n, batch, (double*)UL, Ud, (double*)UR, (const double*)VL, Vd, (const double*)VR, ws);
@@ -821,7 +876,7 @@ int sla_rmul_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, doub
 int sla_lmul_ldr_mat(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
                      void* V, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -9;
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return lmul_ldr_mat_impl<double>(h, n, batch, (const double*)L, d, (const double*)R, (double*)V, ws);
     return lmul_ldr_mat_impl<cplx>(h, n, batch, (const cplx*)L, d, (const cplx*)R, (cplx*)V, ws);
 }
@@ -829,21 +884,21 @@ int sla_lmul_ldr_mat(sla_handle_t h, int dtype, int n, int batch, const void* L,
 int sla_rmul_mat_ldr(sla_handle_t h, int dtype, int n, int batch, void* U, const void* L, const double* d,
                      const void* R, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!U) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9;
+    if (!U) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return rmul_mat_ldr_impl<double>(h, n, batch, (double*)U, (const double*)L, d, (const double*)R, ws);
     return rmul_mat_ldr_impl<cplx>(h, n, batch, (cplx*)U, (const cplx*)L, d, (const cplx*)R, ws);
 }
 
 int sla_det_lu(sla_handle_t h, int dtype, int n, int batch, void* A, double* logdet, void* sign, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!A) return -5; if (!ws) return -8;
+    if (!A) return -5; if (!ws) return -8; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return det_lu_impl<double>(h, n, batch, (double*)A, logdet, (double*)sign, ws);
     return det_lu_impl<cplx>(h, n, batch, (cplx*)A, logdet, (cplx*)sign, ws);
 }
 
 int sla_inv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, double* logdet, void* sign, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!A) return -5; if (!ws) return -8;
+    if (!A) return -5; if (!ws) return -8; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return inv_lu_impl<double>(h, n, batch, (double*)A, logdet, (double*)sign, ws);
     return inv_lu_impl<cplx>(h, n, batch, (cplx*)A, logdet, (cplx*)sign, ws);
 }
@@ -851,7 +906,7 @@ int sla_inv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, double* log
 int sla_logabsdet(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
                   double* logdet, void* sign, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!ws) return -10;
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return logabsdet_impl<double>(h, n, batch, (const double*)L, d, (const double*)R, logdet, (double*)sign, ws);
     return logabsdet_impl<cplx>(h, n, batch, (const cplx*)L, d, (const cplx*)R, logdet, (cplx*)sign, ws);
 }
@@ -859,14 +914,14 @@ int sla_logabsdet(sla_handle_t h, int dtype, int n, int batch, const void* L, co
 int sla_inv_IpA(sla_handle_t h, int dtype, int n, int batch, void* G, const void* L, const double* d, const void* R,
                 double* logdet, void* sign, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!G) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -11;
+    if (!G) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -11; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return inv_IpA_impl<double>(h, n, batch, (double*)G, (const double*)L, d, (const double*)R, logdet, (double*)sign, ws);
     return inv_IpA_impl<cplx>(h, n, batch, (cplx*)G, (const cplx*)L, d, (const cplx*)R, logdet, (cplx*)sign, ws);
 }
 
 int sla_ldiv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, void* B, double* logdet, void* sign, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!A) return -5; if (!B) return -6; if (!ws) return -9;
+    if (!A) return -5; if (!B) return -6; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldiv_lu_impl<double>(h, n, batch, (double*)A, (double*)B, logdet, (double*)sign, ws);
     return ldiv_lu_impl<cplx>(h, n, batch, (cplx*)A, (cplx*)B, logdet, (cplx*)sign, ws);
 }
@@ -874,7 +929,7 @@ int sla_ldiv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, void* B, d
 int sla_ldiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
                      void* V, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -9;
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldiv_ldr_mat_impl<double>(h, n, batch, (const double*)L, d, (const double*)R, (double*)V, ws);
     return ldiv_ldr_mat_impl<cplx>(h, n, batch, (const cplx*)L, d, (const cplx*)R, (cplx*)V, ws);
 }
@@ -883,7 +938,7 @@ int sla_ldiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, const void* UL
                      void* VL, double* Vd, void* VR, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
     UV_NULLCHECK();
-    if (!ws) return -11;
+    if (!ws) return -11; CLEAR_INFO(h, dtype, n, batch, ws);
     if (UL == VL || UR == VR || Ud == Vd) return -8;
     if (dtype == SLA_F64)
         return ldiv_ldr_ldr_impl<double>(h, n, batch, (const double*)UL, Ud, (const double*)UR, (double*)VL, Vd, (double*)VR, ws);
@@ -893,7 +948,7 @@ int sla_ldiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, const void* UL
 int sla_ldiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U, long long strideU, void* L, double* d,
                      void* R, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!U) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10;
+    if (!U) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldiv_mat_ldr_impl<double>(h, n, batch, (const double*)U, strideU, (double*)L, d, (double*)R, ws);
     return ldiv_mat_ldr_impl<cplx>(h, n, batch, (const cplx*)U, strideU, (cplx*)L, d, (cplx*)R, ws);
 }
@@ -901,7 +956,7 @@ int sla_ldiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U,
 int sla_rdiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, void* U, const void* L, const double* d,
                      const void* R, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!U) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9;
+    if (!U) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return rdiv_mat_ldr_impl<double>(h, n, batch, (double*)U, (const double*)L, d, (const double*)R, ws);
     return rdiv_mat_ldr_impl<cplx>(h, n, batch, (cplx*)U, (const cplx*)L, d, (const cplx*)R, ws);
 }
@@ -910,7 +965,7 @@ int sla_rdiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, doub
                      const double* Vd, const void* VR, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
     UV_NULLCHECK();
-    if (!ws) return -11;
+    if (!ws) return -11; CLEAR_INFO(h, dtype, n, batch, ws);
     if (UL == VL || UR == VR || Ud == Vd) return -8;
     if (dtype == SLA_F64)
         return rdiv_ldr_ldr_impl<double>(h, n, batch, (double*)UL, Ud, (double*)UR, (const double*)VL, Vd, (const double*)VR, ws);
@@ -920,7 +975,7 @@ int sla_rdiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, doub
 int sla_rdiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R, const void* V,
                      long long strideV, void* ws) {
     CHECK_COMMON(h, dtype, n, batch);
-    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -10;
+    if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return rdiv_ldr_mat_impl<double>(h, n, batch, (double*)L, d, (double*)R, (const double*)V, strideV, ws);
     return rdiv_ldr_mat_impl<cplx>(h, n, batch, (cplx*)L, d, (cplx*)R, (const cplx*)V, strideV, ws);
 }
@@ -931,7 +986,7 @@ int sla_rdiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, void* L, doubl
         CHECK_COMMON(h, dtype, n, batch);                                                                          \
         if (!G) return -5;                                                                                         \
         if (!UL) return -6; if (!Ud) return -7; if (!UR) return -8; if (!VL) return -9; if (!Vd) return -10;       \
-        if (!VR) return -11; if (!ws) return -14;                                                                  \
+        if (!VR) return -11; if (!ws) return -14; CLEAR_INFO(h, dtype, n, batch, ws);                                                                  \
         if (dtype == SLA_F64)                                                                                      \
             return impl<double>(h, n, batch, (double*)G, (const double*)UL, Ud, (const double*)UR, (const double*)VL, \
                                 Vd, (const double*)VR, logdet, (double*)sign, ws);                                 \
@@ -946,6 +1001,7 @@ int sla_gemm(sla_handle_t h, int dtype, int opa, int opb, int m, int n, int k, c
              long long strideA, const void* B, int ldb, long long strideB, void* C, int ldc, long long strideC,
              int batch, int accumulate) {
     if (!h) return -1;
+    if (!device_is_current(h)) return SLA_EDEVICE;
     if (dtype != SLA_F64 && dtype != SLA_C64) return -2;
     if ((opa != SLA_OP_N && opa != SLA_OP_C)) return -3;
     if ((opb != SLA_OP_N && opb != SLA_OP_C)) return -4;
@@ -971,9 +1027,27 @@ int sla_gemm(sla_handle_t h, int dtype, int opa, int opb, int m, int n, int k, c
     return 0;
 }
 
+int sla_walker_sums(sla_handle_t h, int dtype, int batch, const double* logdet, const void* sign, double* out4) {
+    if (!h) return -1;
+    if (!device_is_current(h)) return SLA_EDEVICE;
+    if (dtype != SLA_F64 && dtype != SLA_C64) return -2;
+    if (batch < 0) return -3;
+    if (!logdet) return -4; if (!sign) return -5; if (!out4) return -6;
+    if (dtype == SLA_F64) CK(walker_sums_batched<double>(out4, logdet, (const double*)sign, batch, h->stream));
+    else CK(walker_sums_batched<cplx>(out4, logdet, (const cplx*)sign, batch, h->stream));
+    return 0;
+}
+
 size_t sla_greens_chain_workspace_bytes(int dtype, int n, int batch, int L, int n_stab) {
     if (n <= 0 || batch <= 0 || L <= 0 || n_stab <= 0 || L % n_stab) return 0;
+    if ((dtype != SLA_F64 && dtype != SLA_C64) || !n_supported(dtype, n)) return 0;
     return dtype == SLA_F64 ? ChainWs<double>::bytes(n, batch, L, n_stab) : ChainWs<cplx>::bytes(n, batch, L, n_stab);
+}
+
+int* sla_greens_chain_workspace_info(void* ws, int dtype, int n, int batch, int L, int n_stab) {
+    if (!ws || n <= 0 || batch <= 0 || L <= 0 || n_stab <= 0 || L % n_stab) return nullptr;
+    if (dtype == SLA_F64) return Ws<double>(ChainWs<double>(ws, n, batch, L, n_stab).ws, n, batch).info;
+    return Ws<cplx>(ChainWs<cplx>(ws, n, batch, L, n_stab).ws, n, batch).info;
 }
 
 int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L, int n_stab, const void* expK,

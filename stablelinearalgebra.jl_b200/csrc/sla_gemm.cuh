@@ -14,12 +14,17 @@
 // fragment reads (lane t -> [t/4][t%4]) are bank-conflict free for both operand orientations.
 // Complex GEMM runs 4 real DMMAs per tile pair on the interleaved (re,im) data.
 #pragma once
+#include <atomic>
+
 #include "sla_common.cuh"
 
 namespace sla {
 
 // number of kernels this library has launched in this process (bench.py reports it as gpu_launches)
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;
+
+constexpr int kMaxDevices = 64;
+inline int current_device() { int d = -1; return cudaGetDevice(&d) == cudaSuccess ? d : -1; }
 
 enum Op : int { OP_N = 0, OP_C = 1 };  // OP_C = conjugate transpose (plain transpose for real)
 
@@ -266,11 +271,13 @@ static cudaError_t launch_gemm_vec(const GemmArgs<T>& p, cudaStream_t stream) {
     constexpr int SMEM = STAGES * (TileA::ELEMS + TileB::ELEMS) * (int)sizeof(T);
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     auto kern = gemm_kernel<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES, VEC>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
+    // the attribute is per device (context): cached per instantiation AND device ordinal
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
     int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
     if (tiles <= 0 || p.batch <= 0) return cudaSuccess;

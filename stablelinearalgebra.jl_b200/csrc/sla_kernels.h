@@ -15,8 +15,19 @@ template <typename T> struct LdrArgs {
     T* Twork; long long strideT;             // scratch: ldr_twork_elems(n) elements per matrix
     long long* jpvt_out;                     // optional: 1-based pivots (n per matrix), may be null
     long long* prof;                         // optional (diagnostics): per-phase cycle counters of cluster 0, may be null
+    int* info;                               // optional per-matrix info: raised from 0 to LDR_INFO_RANGE (never cleared here)
     int n; int batch;
 };
+// Column norms are carried SQUARED (no sqrt on the per-column critical path), unlike ?nrm2 which is safe to 1e+-308:
+// a column whose squared norm overflows, is NaN, or underflows although the column is not zero is reported through
+// info (include/sla_b200.h: SLA_INFO_RANGE) instead of being mis-pivoted silently.
+constexpr int LDR_INFO_RANGE = -1;
+__device__ __forceinline__ bool ldr_norm2_out_of_range(double ssq, bool column_nonzero) {
+    return !(ssq < 1e300) || (column_nonzero && ssq < 1e-290);
+}
+__device__ __forceinline__ void ldr_raise_range(int* info, int b) {
+    if (info) atomicCAS(info + b, 0, LDR_INFO_RANGE);
+}
 template <typename T> cudaError_t ldr_batched(const LdrArgs<T>& p, cudaStream_t s);
 template <typename T> size_t ldr_twork_elems(int n);
 // on-chip (thread-block cluster + DSMEM) version, sla_ldr_cluster.cu; cluster size 0 = matrix too large
@@ -44,6 +55,7 @@ template <typename T> struct LuArgs {
     int n; int batch;
 };
 template <typename T> cudaError_t lu_batched(const LuArgs<T>& p, cudaStream_t s);
+template <typename T> bool lu_supported(int n);   // the panels of an n x n matrix fit the shared memory of one CTA
 
 // ---- element-wise / small kernels (sla_ops.cu) ---------------------------------------------
 // dst = rowscale(rs) * op(src) * colscale(cs); src may be shared (stride 0); op in {OP_N, OP_C}
@@ -66,6 +78,8 @@ template <typename T> struct CombineArgs {
     double* logdet; T* sign; int batch;
 };
 template <typename T> cudaError_t combine_batched(const CombineArgs<T>& a, cudaStream_t s);
+// out4 = [sum logdet, sum Re sign, sum Im sign, batch] (local part of the cross-walker all-reduce)
+template <typename T> cudaError_t walker_sums_batched(double* out4, const double* logdet, const T* sign, int batch, cudaStream_t s);
 // out[i] = multiplier realising ScaleMode `mode` with d[i] (feeds the GEMM epilogue, which only multiplies)
 cudaError_t scale_prep_batched(double* out, const double* d, int mode, long long count, cudaStream_t s);
 // ev[c,l,i] = exp(lam * s[c,l,i])

@@ -174,12 +174,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
         const T* col = Ain ? Ain + (long long)c * p.ldain : A + (long long)c * lda;
         T* dcol = A + (long long)c * lda;
         double acc = 0.0;
+        bool nz = false;
         for (int r = lane; r < n; r += 32) {
             T x = col[r];
             if (Ain) dcol[r] = x;
             acc += abs2_(x);
+            nz |= !is_zero(x);
         }
         acc = warp_sum(acc);
+        nz = __any_sync(0xffffffffu, nz);
+        if (lane == 0 && ldr_norm2_out_of_range(acc, nz)) ldr_raise_range(p.info, b);
         if (lane == 0) { double nr = sqrt(acc); s.vn1[c] = nr; s.vn2[c] = nr; s.jpvt[c] = c; }
     }
     __syncthreads();

@@ -186,18 +186,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_cluster_kernel(LdrArgs<T> 
         const int c = lc * CS + rank;
         T* col = A + (size_t)lc * ldc;
         double acc = 0.0;
+        bool nz = false;
         if (c < n) {
             const T* src = Ain + (long long)c * ldin;
             for (int r = lane; r < ldc; r += 32) {
                 T x = (r < n) ? src[r] : mk<T>(0.0);
                 col[r] = x;
                 acc += abs2_(x);
+                nz |= !is_zero(x);
             }
         } else {
             for (int r = lane; r < ldc; r += 32) col[r] = mk<T>(0.0);
         }
         acc = warp_sum(acc);
+        nz = __any_sync(0xffffffffu, nz);
         if (lane == 0) {
+            if (c < n && ldr_norm2_out_of_range(acc, nz)) ldr_raise_range(p.info, b);
             vn1[lc] = acc; vn2[lc] = acc;   // SQUARED partial norms (no sqrt on the per-column critical path)
             pos[lc] = (c < n) ? -1 : n;   // padding columns count as already chosen
             wbuf[lc] = mk<T>(0.0); wbuf[nloc + lc] = mk<T>(0.0);

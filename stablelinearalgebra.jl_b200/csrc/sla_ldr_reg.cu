@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     long long tq = 0;
 #endif
     if constexpr (MODE != 2) {
-    unsigned active = 0;
+    unsigned active = 0, nzmask = 0;
     double ssq[TOT];
 #pragma unroll
     for (int u = 0; u < TOT; ++u) {
@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
             const int r = lane + 32 * t;
             const T val = (c < n && r < n) ? src[r] : mk<T>(0.0);
             ssq[u] += abs2_(val);
+            if (!is_zero(val)) nzmask |= 1u << u;
             if (u < CPW) a[u < CPW ? u : 0][t] = val;
             else sst(u - CPW, t, val);
         }
@@ -251,6 +252,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_reg_kernel(LdrArgs<T> p) {
     double vn1 = reduce_transposed<double, TOT>(ssq, lane);
     double rvn1 = 1.0 / vn1, q12 = 1.0;
     const int myc = colof(myu);
+    {   // range guard of the squared norms (sla_kernels.h)
+        nzmask = __reduce_or_sync(0xffffffffu, nzmask);
+        const bool bad = ((active >> myu) & 1u) && ldr_norm2_out_of_range(vn1, (nzmask >> myu) & 1u);
+        if (__any_sync(0xffffffffu, bad) && lane == 0) ldr_raise_range(p.info, b);
+    }
     const int n_al = (n + EPV - 1) & ~(EPV - 1);
     constexpr int NKEY = CTA_WARPS * TOT;   // one key slot per (warp, column)
     constexpr int KPL = NKEY / 32;          // keys a lane scans

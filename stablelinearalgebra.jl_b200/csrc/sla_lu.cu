@@ -17,6 +17,10 @@ namespace sla {
 
 namespace {
 
+// a NaN/Inf pivot means an earlier factorisation of the same composite call was singular: report it like a zero pivot
+__device__ __forceinline__ bool lu_finite(double x) { return fabs(x) <= 1.7976931348623157e308; }
+__device__ __forceinline__ bool lu_finite(cplx x) { return lu_finite(x.re) && lu_finite(x.im); }
+
 constexpr int LU_NB = 32;
 
 template <typename T> __host__ __device__ inline size_t lu_smem_bytes(int n, int NB) {
@@ -123,9 +127,10 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
                         }
                     }
                     const T pv = rowP[j];
-                    if (is_zero(pv)) {
+                    if (is_zero(pv) || !lu_finite(pv)) {
                         if (tid == 0 && info_out && *info_out == 0) *info_out = k + 1;
-                    } else if (r > k && r < n) {
+                    }
+                    if (!is_zero(pv) && r > k && r < n) {
                         T l;
                         if constexpr (!is_cplx<T>::value) {   // reciprocal scaling like ?getf2 (division below sfmin)
                             if (fabs(pv) >= 2.2250738585072014e-308) l = arow[j] * __drcp_rn(pv);
@@ -170,9 +175,10 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
                 if (tid == 0) ipiv[k] = piv;
                 __syncthreads();
                 const T pv = colj[k];
-                if (is_zero(pv)) {
+                if (is_zero(pv) || !lu_finite(pv)) {
                     if (tid == 0 && info_out && *info_out == 0) *info_out = k + 1;
-                } else {
+                }
+                if (!is_zero(pv)) {
                     for (int r = k + 1 + tid; r < n; r += CTA_THREADS) {
                         T l = colj[r] / pv;
                         colj[r] = l;
@@ -390,9 +396,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) lu_kernel(LuArgs<T> p) {
     int* misc = redi + 32;
 
     T* A = p.A + (long long)b * p.strideA;
+    // info is cleared once per C-API entry point (sla_capi.cu: clear_info), not per kernel: composite calls run two or
+    // three LU factorisations and the FIRST failure has to survive (the reference throws at every getrf!, lu.jl:75)
     int* info = p.info ? p.info + b : nullptr;
-    if (info && tid == 0) *info = 0;
-    __syncthreads();
     lu_factor<T, NB>(A, p.lda, n, Ps, Us, ld, ipiv, rowpos, tl, tsrc, redv, redi, misc, info);
     double logdet; T sgn;
     lu_logdet<T>(A, p.lda, n, ipiv, redv, redt, logdet, sgn);
@@ -439,6 +445,12 @@ template <typename T> cudaError_t lu_batched(const LuArgs<T>& p, cudaStream_t st
     if (nb == 16) return launch(lu_kernel<T, 16>);
     return launch(lu_kernel<T, 8>);
 }
+
+template <typename T> bool lu_supported(int n) {
+    return n > 0 && lu_smem_bytes<T>(n, 8) <= (size_t)227 * 1024;
+}
+template bool lu_supported<double>(int);
+template bool lu_supported<cplx>(int);
 
 template cudaError_t lu_batched<double>(const LuArgs<double>&, cudaStream_t);
 template cudaError_t lu_batched<cplx>(const LuArgs<cplx>&, cudaStream_t);

@@ -5,7 +5,7 @@
 
 namespace sla {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 namespace {
 
@@ -140,6 +140,29 @@ __global__ void hs_exp_kernel(double* ev, const signed char* f, double ep, doubl
     if (i < count) ev[i] = f[i] > 0 ? ep : em;
 }
 
+// out[0..3] = [sum logdet, sum Re sign, sum Im sign, batch]: the local part of the cross-walker reduction, in a FIXED
+// summation order (one block, strided partial sums, tree over warps) so that the result does not depend on timing
+template <typename T> __global__ void walker_sums_kernel(double* out, const double* logdet, const T* sign, int batch) {
+    __shared__ double red[3][32];
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = threadIdx.x; i < batch; i += blockDim.x) {
+        a += logdet[i];
+        b += real_(sign[i]);
+        c += imag_(sign[i]);
+    }
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; red[2][threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = blockDim.x >> 5;
+        a = threadIdx.x < nw ? red[0][threadIdx.x] : 0.0;
+        b = threadIdx.x < nw ? red[1][threadIdx.x] : 0.0;
+        c = threadIdx.x < nw ? red[2][threadIdx.x] : 0.0;
+        a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+        if (threadIdx.x == 0) { out[0] = a; out[1] = b; out[2] = c; out[3] = (double)batch; }
+    }
+}
+
 inline dim3 grid_rows_cols(int n, int batch, int threads) {
     return dim3((n + threads - 1) / threads, min(n, 64), batch);
 }
@@ -220,6 +243,14 @@ cudaError_t hs_exp_batched(double* ev, const signed char* fields, double lam, lo
     ++g_launch_count;
     return cudaGetLastError();
 }
+
+template <typename T> cudaError_t walker_sums_batched(double* out4, const double* logdet, const T* sign, int batch, cudaStream_t s) {
+    walker_sums_kernel<T><<<1, 256, 0, s>>>(out4, logdet, sign, batch);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+template cudaError_t walker_sums_batched<double>(double*, const double*, const double*, int, cudaStream_t);
+template cudaError_t walker_sums_batched<cplx>(double*, const double*, const cplx*, int, cudaStream_t);
 
 #define INST(T)                                                                                                   \
     template cudaError_t scale_batched<T>(T*, long long, int, const T*, long long, int, int, const double*,      \

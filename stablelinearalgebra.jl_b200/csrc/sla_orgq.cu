@@ -250,11 +250,12 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
 cudaError_t orgq_dmma_batched(const LdrArgs<double>& p, cudaStream_t stream) {
     if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
     if (p.n > 256 || p.Twork == nullptr || p.strideT < p.n) return cudaErrorNotSupported;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};   // the attribute is per device
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(orgq_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OQ_SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)p.batch * 4, 1, 1);

@@ -27,9 +27,16 @@ def weak_chain_ids(chains_per_rank: int, rank: int) -> range:
 
 def reduce_walkers(logdet: torch.Tensor, sign: torch.Tensor, out: torch.Tensor | None = None, group=None):
     """Cross-walker sums [sum logdet, sum Re(sign), sum Im(sign), count], all-reduced over the ranks.
-    Runs on the tensors' device and stream (NCCL orders the collective on the current stream)."""
+    Runs on the tensors' device and stream (NCCL orders the collective on the current stream).  On a GPU the local sums
+    are ONE library kernel (``sla_walker_sums``) writing the 4-double buffer that goes straight into the all-reduce."""
     if out is None:
         out = torch.zeros(4, dtype=torch.float64, device=logdet.device)
+    if logdet.is_cuda:
+        from . import api
+        api.walker_sums(logdet, sign, out)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(out, group=group)
+        return out
     s = sign.sum()
     vals = [logdet.sum(), s.real if sign.is_complex() else s,
             s.imag if sign.is_complex() else torch.zeros((), dtype=torch.float64, device=logdet.device),

@@ -191,6 +191,69 @@ def test_lu_singular_info(S):
         S.check_info(ws)
 
 
+def test_info_survives_composite_calls(S):
+    """A singular R inside a composite call (three LU factorisations: L_u, R_v, M) must be reported even though the
+    LAST factorisation sees only NaNs (the reference throws at the failing getrf!, src/lu.jl:75)."""
+    rng = np.random.default_rng(11)
+    n, batch = 24, 3
+    A = rand_matrix(rng, n, False, batch)
+    dA = S.to_device(A)
+    ws = S.ldr_workspace(dA)
+    U, V = S.ldr(dA, ws), S.ldr(dA, ws)
+    V.R[1].zero_()                      # R_v of batch entry 1 exactly singular
+    G = torch.empty_like(dA)
+    S.inv_IpUV_(G, U, V, ws)
+    info = ws.info().cpu().numpy()
+    assert info[0] == 0 and info[2] == 0 and info[1] > 0
+    with pytest.raises(np.linalg.LinAlgError):
+        S.check_info(ws)
+    S.inv_IpA_(G, U, ws)                # the next entry point starts from a clean slate
+    assert not ws.info().cpu().numpy().any()
+    S.check_info(ws)
+
+
+@pytest.mark.parametrize("n", [48, 200, 300, 600])
+def test_ldr_norm_range_guard(S, n):
+    """Column norms are carried squared: inputs whose squared norms leave the double range are flagged through info
+    (SLA_INFO_RANGE) by every LDR kernel family instead of being mis-pivoted silently; in-range inputs are not."""
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((3, n, n))
+    A[1, :, n // 2] *= 1e160            # squared norm overflows
+    A[2, :, 1] *= 1e-170                # squared norm underflows to 0 although the column is not zero
+    dA = S.to_device(A)
+    ws = S.ldr_workspace(dA)
+    S.ldr(dA, ws)
+    info = ws.info().cpu().numpy()
+    assert list(info) == [0, -1, -1], info
+    with pytest.raises(np.linalg.LinAlgError):
+        S.check_info(ws)
+    B = rng.standard_normal((3, n, n)) * (10.0 ** np.linspace(140, -140, n))[None, None, :]
+    dB = S.to_device(B)
+    S.ldr(dB, ws)
+    assert not ws.info().cpu().numpy().any()
+
+
+def test_unsupported_size_and_argument_validation(S):
+    lib = S.load()
+    nmax = lib.sla_max_n(0)
+    assert 1024 <= nmax < 4096 and lib.sla_max_n(1) < nmax
+    assert lib.sla_workspace_bytes(0, nmax, 1) > 0 and lib.sla_workspace_bytes(0, nmax + 1, 1) == 0
+    with pytest.raises(S.SlaError):
+        S.LDRWorkspace(nmax + 1, 1, torch.float64)
+    A = S.to_device(np.eye(8)[None].repeat(4, 0))
+    ws = S.ldr_workspace(A)
+    F = S.ldr(A, ws)
+    with pytest.raises(S.SlaError):
+        S.ldr_(F)                                   # no workspace
+    with pytest.raises(S.SlaError):
+        S.lmul_(A[:3], F, ws)                       # batch 3 against 4
+    with pytest.raises(S.SlaError):
+        S.lmul_(A.to(torch.complex128), F, ws)      # eltype mismatch
+    with pytest.raises(S.SlaError):
+        S.inv_IpA_(torch.empty((4, 9, 9), dtype=torch.float64, device="cuda"), F, ws)
+    S.lmul_(A[:1], F, ws)                           # a one-matrix batch is shared: fine
+
+
 # ------------------------------------------------------------- the reference's own test-suite, on GPU
 class Setup:
     """test/runtests.jl:59-100 (4x4 lattice, beta=40, dtau=0.1, n_s=10)."""
@@ -450,6 +513,82 @@ def check_chain(S, cfg, chains, inverse, n_oracle=None):
     return worst
 
 
+def check_chain_full_batch(S, cfg, sample, inverse, expect_algo):
+    """A BASELINE config at its FULL batch (the batch selects the LDR kernel, sla_capi.cu Ctx::ldr): all chains in one
+    call, the sampled chains against the oracle, and an assertion of which factorisation kernel served the call."""
+    before = S.ldr_algo_launches()
+    expK, fields, G, logdet, sign = run_chain(S, cfg, list(range(cfg.chains)), inverse)
+    after = S.ldr_algo_launches()
+    used = {k: after[k] - before[k] for k in after if after[k] != before[k]}
+    assert set(used) == {expect_algo}, f"LDR kernels used: {used}, expected only {expect_algo}"
+    assert used[expect_algo] == cfg.L // cfg.n_stab
+    worst = 0.0
+    for i in sample:
+        Gr, lr, sr, _ = ochain.eval_greens(expK, fields[i], cfg.lam, cfg.n_stab, inverse)
+        e = relerr(G[i], Gr)
+        worst = max(worst, e)
+        assert e < G_TOL, f"chain {i}: max|G-Gref|/max|Gref| = {e:.3e}"
+        assert abs(logdet[i] - lr) <= 1e-10 * max(1.0, abs(lr))
+        if cfg.dtype.kind == "c":
+            assert abs(sign[i] - sr) < 1e-9
+        else:
+            assert sign[i] == sr
+    print(f"[parity] {cfg.name} full batch ({cfg.chains} chains, LDR kernel = {expect_algo}): "
+          f"max rel err G over chains {list(sample)} = {worst:.2e}")
+    return worst
+
+
+# which factorisation kernel the dispatcher must pick at the full batch of each BASELINE config (DESIGN.md section 4)
+BENCH_ALGO = {"C2": "hybrid", "C3": "streaming", "C4": "streaming", "C5": "streaming"}
+
+
+def test_chain_C2_full_batch(S):
+    """C2 exactly as bench.py runs it: 64 chains of N=256, L=200 in ONE call (hybrid shape + tensor-core Q)."""
+    check_chain_full_batch(S, S.synthetic.CONFIGS["C2"], [0, 1, 31, 63], "IpA", BENCH_ALGO["C2"])
+
+
+def test_chain_C3_full_batch(S):
+    """C3 at its full batch: 128 ComplexF64 chains of N=256 through inv_IpUV!."""
+    check_chain_full_batch(S, S.synthetic.CONFIGS["C3"], [0, 127], "IpUV", BENCH_ALGO["C3"])
+
+
+def test_chain_C5_per_gpu_batch(S):
+    """C5's per-GPU share at 8 GPUs: 512 chains of N=400 in one call."""
+    syn = S.synthetic
+    c5 = syn.CONFIGS["C5"]
+    cfg = syn.HubbardConfig("C5/8", c5.Lx, c5.L, c5.n_stab, 512)
+    check_chain_full_batch(S, cfg, [0, 511], "IpA", BENCH_ALGO["C5"])
+
+
+def test_chain_C4_full(S):
+    """C4 as BASELINE states it: N=1024, L=400 (d spans ~1e+-105), all 32 chains in one call; one chain vs the oracle."""
+    check_chain_full_batch(S, S.synthetic.CONFIGS["C4"], [0], "IpA", BENCH_ALGO["C4"])
+
+
+def test_forced_ldr_algo_must_apply():
+    """SLA_LDR_ALGO forces a kernel; where it does not exist for (eltype, n) the call fails with SLA_ENOTIMPL instead of
+    silently running another kernel (child process: the variable is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, sla_b200 as S\n"
+        "A = S.to_device(np.random.default_rng(0).standard_normal((2, 64, 64)))\n"
+        "ws = S.ldr_workspace(A)\n"
+        "try:\n"
+        "    S.ldr(A, ws)\n"
+        "    print('RAN', S.last_ldr_algo())\n"
+        "except S.SlaError as e:\n"
+        "    print('ERR', 'SLA_ENOTIMPL' in str(e))\n"
+        "B = S.to_device(np.random.default_rng(0).standard_normal((2, 200, 200)))\n"
+        "S.ldr(B, S.ldr_workspace(B)); torch.cuda.synchronize(); print('RAN', S.last_ldr_algo())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SLA_LDR_ALGO="hyb", PYTHONPATH=root),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.split("\n")[:2] == ["ERR True", "RAN hybrid"], r.stdout
+
+
 def test_chain_C1(S):
     cfg = S.synthetic.CONFIGS["C1"]           # N=64, L=100: the reference's CPU-runnable case
     check_chain(S, cfg, list(range(4)), "IpA")
@@ -481,6 +620,15 @@ def test_chain_C4_size_short(S):
     # N=1024 (C4's matrix size, L2-streaming LDR kernel) with a short chain so that the CPU oracle stays cheap
     cfg = S.synthetic.HubbardConfig("C4s", 32, 40, 10, 1)
     check_chain(S, cfg, [0], "IpA")
+
+
+@pytest.mark.parametrize("complex_", [False, True])
+def test_walker_sums(S, complex_):
+    rng = np.random.default_rng(3)
+    ld = rng.standard_normal(777)
+    sg = np.exp(1j * rng.uniform(0, 6.28, 777)) if complex_ else np.sign(rng.standard_normal(777))
+    out = S.walker_sums(torch.from_numpy(ld).cuda(), torch.from_numpy(sg).cuda()).cpu().numpy()
+    assert np.allclose(out, [ld.sum(), sg.real.sum(), sg.imag.sum() if complex_ else 0.0, 777], rtol=1e-13, atol=1e-12)
 
 
 def test_chain_sharding_invariance(S):
@@ -565,10 +713,27 @@ def test_other_ldr_kernels_subprocess(algo):
         env["SLA_HYB_SPLITQ"] = "0"
     if algo.endswith("+qvec"):    # Q formed by the vector-unit MODE 2 launch instead of the tensor-core kernel (sla_orgq.cu)
         env["SLA_Q_DMMA"] = "0"
-    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
-                        "ldr_random or ldr_graded or ldr_identity or ldr_hybrid or chain_C1 or ref_lmul_matrix or small_complex"],
+    # only tests whose sizes the forced kernel exists for (a forced kernel that does not apply is an error)
+    if algo.startswith("hyb"):      # real, 128 < n <= 256
+        sel = "ldr_hybrid or ldr_random[256-False] or ldr_graded[256-100-False] or chain_C2_sample or forced_algo_ran"
+    else:
+        sel = ("ldr_random or ldr_graded or ldr_identity or ldr_hybrid or chain_C1 or ref_lmul_matrix or small_complex "
+               "or forced_algo_ran")
+    env["SLA_EXPECT_ALGO"] = {"streaming": "streaming", "cluster": "cluster"}.get(algo, "hybrid")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", sel],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_forced_algo_ran(S):
+    """Runs only inside the SLA_LDR_ALGO child processes (last in their selection): every factorisation of the child was
+    served by the forced kernel."""
+    import os
+    want = os.environ.get("SLA_EXPECT_ALGO")
+    if not want:
+        pytest.skip("not in a forced-algorithm child process")
+    used = {k: v for k, v in S.ldr_algo_launches().items() if v}
+    assert set(used) == {want}, used
 
 
 def test_ldr_n512_and_n1024_paths(S):
