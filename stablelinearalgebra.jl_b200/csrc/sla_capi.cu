@@ -138,7 +138,7 @@ template <typename T> struct Ctx {
             const char* e = getenv("SLA_LDR_ALGO");
             if (getenv("SLA_LDR_STREAMING")) return 3;
             if (!e) return 0;
-            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : (e[0] == 'h' ? 4 : 0)));
+            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : (e[0] == 'h' ? 4 : (e[0] == 'b' ? 5 : 0))));
         }();
         // Cluster kernels minimise latency (one matrix per CS SMs, ~132/CS matrices in flight), the streaming
         // kernel maximises throughput (one matrix per SM, 148 in flight) but is ~4x (register kernel) / ~2.5x
@@ -161,8 +161,16 @@ template <typename T> struct Ctx {
             if (c_reg > 0 && c_hyb > 0) hyb_pays = 100 * waves(batch, c_hyb) < 79 * waves(batch, c_reg);
         }
         // a forced algorithm that does not apply to (T, n) is an error, never a silent fall-through to another kernel
+        // real, 128 < n <= 256: the blocked kernel (?laqps panel of 4 reflectors, DMMA trailing update, clusters of 2) is
+        // correct at every batch size but measured SLOWER than the hybrid shape (0.876 vs 0.688 ms per 64 x N=256
+        // factorisation, profiles/ldr_blk_r2.txt: on B200 the DMMA and the FP64 FMA pipe have the same rate, and the lazy
+        // panel update lengthens the one-warp candidate chain) -- opt-in: SLA_LDR_BLK=1 or SLA_LDR_ALGO=blk
+        static const bool blk_on = getenv("SLA_LDR_BLK") && atoi(getenv("SLA_LDR_BLK")) != 0;
+        const int cs_blk = ldr_blk_cluster_size<T>(n);
         int algo;
-        if (forced == 4) { if (cs_hyb == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_HYBRID; }
+        if (forced == 5) { if (cs_blk == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_BLOCKED; }
+        else if (forced == 0 && blk_on && cs_blk > 0) algo = SLA_LDR_ALGO_BLOCKED;
+        else if (forced == 4) { if (cs_hyb == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_HYBRID; }
         else if (forced == 1) { if (cs_reg == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_REG; }
         else if (forced == 2) { if (cs_cl == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_CLUSTER; }
         else if (forced == 3) algo = SLA_LDR_ALGO_STREAMING;
@@ -172,6 +180,7 @@ template <typename T> struct Ctx {
         else algo = SLA_LDR_ALGO_STREAMING;
         a.info = w.info;
         switch (algo) {
+            case SLA_LDR_ALGO_BLOCKED: CK(ldr_blk_batched<T>(a, s)); break;
             case SLA_LDR_ALGO_HYBRID: CK(ldr_hyb_batched<T>(a, s)); break;
             case SLA_LDR_ALGO_REG: CK(ldr_reg_batched<T>(a, s)); break;
             case SLA_LDR_ALGO_CLUSTER: CK(ldr_cluster_batched<T>(a, s)); break;

@@ -40,6 +40,10 @@ template <typename T> int ldr_reg_cluster_size(int n);
 template <typename T> cudaError_t ldr_hyb_batched(const LdrArgs<T>& p, cudaStream_t s);
 template <typename T> int ldr_hyb_cluster_size(int n);
 void ldr_n256_resident(int* reg_clusters, int* hyb_clusters);
+// blocked panel + tensor-core trailing update (sla_ldr_blk.cu; real, 128 < n <= 256, clusters of 2); 0 = unsupported.
+// Factorises and forms Q (sla_orgq.cu); needs p.Twork with strideT >= n.
+template <typename T> cudaError_t ldr_blk_batched(const LdrArgs<T>& p, cudaStream_t s);
+template <typename T> int ldr_blk_cluster_size(int n);
 // Q = H_0...H_{n-1} I on the FP64 tensor cores after a factorisation-only launch (real, n <= 256; taus in p.Twork)
 cudaError_t orgq_dmma_batched(const LdrArgs<double>& p, cudaStream_t s);
 

@@ -64,3 +64,38 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+
+
+# ---------------------------------------------------------------------------------------------
+# a plain-C client (tests/abi_c/abi_check.c): the header is usable from C, and the calls a Julia `ccall` would make
+# -- same argument types -- give right answers on the GPU
+# ---------------------------------------------------------------------------------------------
+def _build_c_client(sla, tmpdir):
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("CUDA headers not available")
+    exe = os.path.join(str(tmpdir), "abi_check")
+    libdir = os.path.dirname(sla.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-O1", os.path.join(ROOT, "tests", "abi_c", "abi_check.c"),
+           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+           "-L", libdir, "-lsla_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+           "-Wl,-rpath," + libdir, "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_client_compiles_and_links(sla, lib, tmp_path):
+    _build_c_client(sla, tmp_path)
+
+
+@pytest.mark.gpu
+def test_c_client(sla, lib, tmp_path):
+    import subprocess
+    exe = _build_c_client(sla, tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ABI_C_OK" in r.stdout, (r.returncode, r.stdout, r.stderr)

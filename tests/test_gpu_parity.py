@@ -698,7 +698,7 @@ def test_ldr_hybrid_shape_edge_inputs(S):
             assert relerr((L[b] * d[b][None, :]) @ R[b], B[b]) < 1e-12
 
 
-@pytest.mark.parametrize("algo", ["streaming", "cluster", "hyb", "hyb+oneq", "hyb+qvec"])
+@pytest.mark.parametrize("algo", ["streaming", "cluster", "hyb", "hyb+oneq", "hyb+qvec", "blk"])
 def test_other_ldr_kernels_subprocess(algo):
     """Default LDR kernel for n <= 256 is the register-resident cluster kernel.  The shared-memory cluster
     kernel (256 < n <= 512, e.g. C5's N=400) and the L2-streaming kernel (larger n, e.g. C4's N=1024) are
@@ -714,12 +714,12 @@ def test_other_ldr_kernels_subprocess(algo):
     if algo.endswith("+qvec"):    # Q formed by the vector-unit MODE 2 launch instead of the tensor-core kernel (sla_orgq.cu)
         env["SLA_Q_DMMA"] = "0"
     # only tests whose sizes the forced kernel exists for (a forced kernel that does not apply is an error)
-    if algo.startswith("hyb"):      # real, 128 < n <= 256
+    if algo.startswith("hyb") or algo == "blk":      # real, 128 < n <= 256
         sel = "ldr_hybrid or ldr_random[256-False] or ldr_graded[256-100-False] or chain_C2_sample or forced_algo_ran"
     else:
         sel = ("ldr_random or ldr_graded or ldr_identity or ldr_hybrid or chain_C1 or ref_lmul_matrix or small_complex "
                "or forced_algo_ran")
-    env["SLA_EXPECT_ALGO"] = {"streaming": "streaming", "cluster": "cluster"}.get(algo, "hybrid")
+    env["SLA_EXPECT_ALGO"] = {"streaming": "streaming", "cluster": "cluster", "blk": "blocked"}.get(algo, "hybrid")
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", sel],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
