@@ -191,6 +191,22 @@ SLA_API int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L,
                      const signed char* fields, double lam, int inverse, void* G, double* logdet, void* sign,
                      void* Lout, double* dout, void* Rout, void* ws, size_t ws_bytes);
 
+/* Fused DQMC sweep stepper: the caller pattern of inv_IpUV! (exported_functions.jl:97-177) over a
+ * stack of LDR factorisations (the `ldrs` containers of src/LDR.jl:197-257), one upward sweep per chain, fields fixed:
+ *   setup  F_left[ng] = I;  F_left[g] = rmul!(F_left[g+1], B_bar_{g+1})  (overloaded_functions.jl:234-253), all kept;
+ *          G(0) = inv_IpA!(F_left[0])                                   -> G0 (optional), logdet[0][:], sign[0][:]
+ *   sweep  G <- B_l G B_l^-1 for every slice l (B_l^-1 = expK^-1 diag(exp(-lam s_l)));  every n_stab slices
+ *          F_right <- lmul!(B_bar_g, F_right) (overloaded_functions.jl:126-145),
+ *          G' = inv_IpUV!(F_right, F_left[g])                           -> logdet[g][:], sign[g][:],
+ *          dG[g-1][:] = max |G' - G| (the wrap error),  G <- G'.
+ *   G: out, G(beta) (= G(0) up to rounding: the fields are not updated);  logdet: double[ng+1][batch];
+ *   sign: T[ng+1][batch];  dG: double[ng][batch] or NULL;  expKinv: n x n, the inverse of expK. */
+SLA_API size_t sla_sweep_workspace_bytes(int dtype, int n, int batch, int L, int n_stab);
+SLA_API int* sla_sweep_workspace_info(void* ws, int dtype, int n, int batch, int L, int n_stab);
+SLA_API int sla_sweep(sla_handle_t h, int dtype, int n, int batch, int L, int n_stab, const void* expK, const void* expKinv,
+                      const signed char* fields, double lam, void* G0, void* G, double* logdet, void* sign, double* dG,
+                      void* ws, size_t ws_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,9 @@ SIGNATURES = {
     "sla_walker_sums": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "sla_greens_chain_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "sla_greens_chain": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _dbl, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
+    "sla_sweep_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "sla_sweep_workspace_info": (_vp, [_vp, _i, _i, _i, _i, _i]),
+    "sla_sweep": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _sz]),
 }
 
 _lib = None

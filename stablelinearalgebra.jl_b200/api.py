@@ -25,7 +25,7 @@ __all__ = [
     "copyto_", "adjoint_", "lmul_", "rmul_", "mul_", "logabsdet", "det_lu_", "inv_lu_",
     "ldiv_", "rdiv_", "ldiv_lu_",
     "inv_IpA_", "inv_IpUV_", "inv_UpV_", "inv_invUpV_", "gemm", "greens_chain", "check_info",
-    "greens_chain_workspace_bytes", "greens_chain_info", "last_ldr_algo", "ldr_algo_launches", "walker_sums", "SlaError",
+    "greens_chain_workspace_bytes", "greens_chain_info", "sweep", "sweep_info", "last_ldr_algo", "ldr_algo_launches", "walker_sums", "SlaError",
 ]
 
 
@@ -561,3 +561,46 @@ def greens_chain(expK, fields, lam: float, n_stab: int, inverse="IpA", G=None, l
                                 _ptr(logdet), _ptr(sign), _ptr(Lo), _ptr(do), _ptr(Ro), _ptr(ws), ws.numel()),
            "sla_greens_chain")
     return G, logdet, sign, ws
+
+
+def sweep(expK, expKinv, fields, lam: float, n_stab: int, G=None, G0=None, logdet=None, sign=None, dG=None, ws=None):
+    """One stabilised upward sweep per chain (fused stepper ``sla_sweep``): the stack of left
+    factorisations by ``rmul!``, G(0) by ``inv_IpA!``, then per slice the wrap G <- B_l G B_l^-1 and every n_stab
+    slices ``lmul!`` + ``inv_IpUV!(G, F_right, F_left[g])`` (exported_functions.jl:97-177).
+
+    expK / expKinv: column-major device matrices (n, n) or (1, n, n); fields: int8 (batch, L, n).
+    Returns dict(G, G0, logdet[ng+1, batch], sign[ng+1, batch], dG[ng, batch], ws)."""
+    lib, h = _Handle.current()
+    if expK.ndim == 2:
+        expK = expK[None]
+    if expKinv.ndim == 2:
+        expKinv = expKinv[None]
+    batch, L, n = fields.shape
+    if fields.dtype != torch.int8 or expK.shape[1:] != (n, n) or expKinv.shape != expK.shape or expKinv.dtype != expK.dtype:
+        raise ValueError("sweep: expK / expKinv must be (n, n) of one element type and fields int8 (batch, L, n)")
+    if n_stab <= 0 or L % n_stab:
+        raise ValueError("sweep: L must be a multiple of n_stab")
+    ng = L // n_stab
+    dt, dev, code = expK.dtype, expK.device, _dtype_code(expK)
+    G = torch.empty((batch, n, n), dtype=dt, device=dev) if G is None else G
+    G0 = torch.empty((batch, n, n), dtype=dt, device=dev) if G0 is None else G0
+    logdet = torch.empty((ng + 1, batch), dtype=torch.float64, device=dev) if logdet is None else logdet
+    sign = torch.empty((ng + 1, batch), dtype=dt, device=dev) if sign is None else sign
+    dG = torch.empty((ng, batch), dtype=torch.float64, device=dev) if dG is None else dG
+    need = lib.sla_sweep_workspace_bytes(code, n, batch, L, n_stab)
+    if need == 0:
+        raise SlaError(f"sweep: unsupported size n={n}")
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    _check(lib.sla_sweep(h, code, n, batch, L, n_stab, _ptr(expK), _ptr(expKinv), _ptr(fields), float(lam), _ptr(G0),
+                         _ptr(G), _ptr(logdet), _ptr(sign), _ptr(dG), _ptr(ws), ws.numel()), "sla_sweep")
+    return {"G": G, "G0": G0, "logdet": logdet, "sign": sign, "dG": dG, "ws": ws}
+
+
+def sweep_info(ws: torch.Tensor, dtype: torch.dtype, n: int, batch: int, L: int, n_stab: int) -> torch.Tensor:
+    """The per-chain info codes inside a ``sweep`` workspace blob (same meaning as ``LDRWorkspace.info``)."""
+    lib = _lib.load()
+    code = _lib.SLA_F64 if dtype == torch.float64 else _lib.SLA_C64
+    p = lib.sla_sweep_workspace_info(C.c_void_p(ws.data_ptr()), code, n, batch, L, n_stab)
+    off = p - ws.data_ptr()
+    return ws[off:off + 4 * batch].view(torch.int32)

@@ -690,6 +690,140 @@ int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const
     return inv_IpUV_impl<T>(h, n, batch, G, UL, Ud, UR, FL, Fd, FR, logdet, sign, cw.ws);
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused sweep stepper: the caller pattern of inv_IpUV! over stacks of LDR factorisations
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct SweepWs {
+    double *ev, *evi;          // exp(+lam s), exp(-lam s): [batch][L][n]
+    T *B0, *B1;                // group products, ping-pong: [ng][batch][n][n]
+    T *SL, *SR; double* Sd;    // the stack of left factorisations F_left[0..ng]: [ng+1][batch] x (L, d, R)
+    T *RL, *RR, *RR2; double* Rd;   // the right factorisation B(tau_g, 0) (ping-pong R)
+    T *Ga, *Gb;                // wrapped / re-stabilised Green's function
+    void* ws;
+    static size_t bytes(int n, int batch, int L, int n_stab) {
+        const int ng = L / n_stab;
+        const size_t nn = align_up((size_t)n * n * batch * sizeof(T));
+        const size_t nd = align_up((size_t)n * batch * sizeof(double));
+        size_t b = 2 * align_up((size_t)batch * L * n * sizeof(double));
+        b += 2 * align_up((size_t)ng * batch * n * n * sizeof(T));
+        b += 2 * (size_t)(ng + 1) * nn + (size_t)(ng + 1) * nd;
+        b += 3 * nn + nd;
+        b += 2 * nn;
+        b += Ws<T>::bytes(n, batch);
+        return b;
+    }
+    SweepWs(void* blob, int n, int batch, int L, int n_stab) {
+        const int ng = L / n_stab;
+        char* p = static_cast<char*>(blob);
+        const size_t nn = align_up((size_t)n * n * batch * sizeof(T));
+        const size_t nd = align_up((size_t)n * batch * sizeof(double));
+        const size_t ne = align_up((size_t)batch * L * n * sizeof(double));
+        const size_t nb = align_up((size_t)ng * batch * n * n * sizeof(T));
+        ev = (double*)p; p += ne; evi = (double*)p; p += ne;
+        B0 = (T*)p; p += nb; B1 = (T*)p; p += nb;
+        SL = (T*)p; p += (size_t)(ng + 1) * nn; SR = (T*)p; p += (size_t)(ng + 1) * nn;
+        Sd = (double*)p; p += (size_t)(ng + 1) * nd;
+        RL = (T*)p; p += nn; RR = (T*)p; p += nn; RR2 = (T*)p; p += nn;
+        Rd = (double*)p; p += nd;
+        Ga = (T*)p; p += nn; Gb = (T*)p; p += nn;
+        ws = p;
+    }
+    T* sl(int g, int n, int batch) const { return (T*)((char*)SL + (size_t)g * align_up((size_t)n * n * batch * sizeof(T))); }
+    T* sr(int g, int n, int batch) const { return (T*)((char*)SR + (size_t)g * align_up((size_t)n * n * batch * sizeof(T))); }
+    double* sd(int g, int n, int batch) const { return (double*)((char*)Sd + (size_t)g * align_up((size_t)n * batch * sizeof(double))); }
+};
+
+// One upward sweep per chain, fields fixed (restated on the CPU in oracle/sweep.py):
+//   setup  F_left[ng] = I;  F_left[g] = F_left[g+1] * B_bar_{g+1}   rmul!(LDR, Matrix)  overloaded_functions.jl:234-253
+//          G(0) = inv_IpA!(F_left[0])                                                   exported_functions.jl:25-71
+//   sweep  G <- B_l G B_l^-1 for every slice (two GEMMs with the diagonal factors fused into their epilogues);
+//          every n_stab slices  F_right <- lmul!(B_bar_g, F_right)                      overloaded_functions.jl:126-145
+//                               G' = inv_IpUV!(F_right, F_left[g])                      exported_functions.jl:97-177
+//                               dG[g] = max|G' - G|,  G <- G'
+template <typename T>
+int sweep_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const T* expK, const T* expKinv, const signed char* fields,
+               double lam, T* G0, T* G, double* logdet, T* sign, double* dG, void* blob, size_t blob_bytes) {
+    if (blob_bytes < SweepWs<T>::bytes(n, batch, L, n_stab)) return -17;
+    SweepWs<T> sw(blob, n, batch, L, n_stab);
+    Ctx<T> c(h, n, batch, sw.ws);
+    const int ng = L / n_stab;
+    const long long nn = c.nn;
+    cudaStream_t s = c.s;
+    CK(cudaMemsetAsync(c.w.info, 0, (size_t)batch * sizeof(int), s));
+    CK(hs_exp_batched(sw.ev, fields, lam, (long long)batch * L * n, s));
+    CK(hs_exp_batched(sw.evi, fields, -lam, (long long)batch * L * n, s));
+
+    // ---- group products of every group at once (group-major: product of (group g, chain b) at index g*batch + b)
+    T* fin = ((n_stab - 1) & 1) ? sw.B1 : sw.B0;
+    {
+        T *cur = sw.B0, *nxt = sw.B1;
+        for (int i = 0; i < n_stab; ++i) {
+            if (i == 0) {
+                for (int g = 0; g < ng; ++g)
+                    CK(scale_batched<T>(cur + (long long)g * batch * nn, nn, n, expK, 0, n, OP_N,
+                                        sw.ev + ((long long)g * n_stab) * n, (long long)L * n, SCALE_MUL, nullptr, 0, SCALE_NONE,
+                                        n, batch, s));
+                continue;
+            }
+            GemmArgs<T> g{};
+            g.A = expK; g.strideA = 0; g.lda = n;
+            g.B = cur; g.strideB = nn; g.ldb = n;
+            g.C = nxt; g.strideC = nn; g.ldc = n;
+            g.M = g.N = g.K = n;
+            g.rs = sw.ev + (long long)i * n; g.rs_mode = SCALE_MUL; g.rs_div = batch; g.stride_rs_hi = (long long)n_stab * n;
+            g.stride_rs = (long long)L * n;
+            g.batch = batch * ng;
+            CK(gemm_batched<T>(OP_N, OP_N, g, s));
+            T* t = cur; cur = nxt; nxt = t;
+        }
+    }
+    // ---- setup: the stack of left factorisations, from the top of the chain downwards (no copies: slot g+1 -> slot g)
+    CKI(set_identity_impl<T>(h, n, batch, sw.sl(ng, n, batch), sw.sd(ng, n, batch), sw.sr(ng, n, batch)));
+    for (int g = ng - 1; g >= 0; --g) {
+        const T* Bg = fin + (long long)g * batch * nn;
+        CKI(c.gemm(c.w.M, OP_N, sw.sr(g + 1, n, batch), nn, OP_N, Bg, nn, sw.sd(g + 1, n, batch), SCALE_MUL));   // Du (Ru V)   (:241-243)
+        CKI(c.ldr(c.w.M, sw.sd(g, n, batch), sw.sr(g, n, batch)));                                                // ldr!        (:246)
+        CKI(c.gemm(sw.sl(g, n, batch), OP_N, sw.sl(g + 1, n, batch), nn, OP_N, c.w.M, nn));                        // Lu L0       (:249)
+    }
+    T *Gw = sw.Ga, *Gs = sw.Gb;
+    CKI(inv_IpA_impl<T>(h, n, batch, Gw, sw.sl(0, n, batch), sw.sd(0, n, batch), sw.sr(0, n, batch), logdet, sign, sw.ws));
+    if (G0) CKI(c.copy(G0, Gw));
+    // ---- sweep
+    T *RL = sw.RL, *RR = sw.RR, *RR2 = sw.RR2;
+    CKI(set_identity_impl<T>(h, n, batch, RL, sw.Rd, RR));
+    for (int g = 0; g < ng; ++g) {
+        for (int i = 0; i < n_stab; ++i) {
+            const long long l = (long long)g * n_stab + i;
+            GemmArgs<T> a{};                 // T1 = diag(e_l) (expK G)
+            a.A = expK; a.strideA = 0; a.lda = n;
+            a.B = Gw; a.strideB = nn; a.ldb = n;
+            a.C = c.w.M; a.strideC = nn; a.ldc = n;
+            a.M = a.N = a.K = n;
+            a.rs = sw.ev + l * n; a.stride_rs = (long long)L * n; a.rs_mode = SCALE_MUL;
+            a.batch = batch;
+            CK(gemm_batched<T>(OP_N, OP_N, a, s));
+            GemmArgs<T> b2{};                // G = (T1 expK^-1) diag(1 / e_l)
+            b2.A = c.w.M; b2.strideA = nn; b2.lda = n;
+            b2.B = expKinv; b2.strideB = 0; b2.ldb = n;
+            b2.C = Gw; b2.strideC = nn; b2.ldc = n;
+            b2.M = b2.N = b2.K = n;
+            b2.cs = sw.evi + l * n; b2.stride_cs = (long long)L * n; b2.cs_mode = SCALE_MUL;
+            b2.batch = batch;
+            CK(gemm_batched<T>(OP_N, OP_N, b2, s));
+        }
+        const T* Bg = fin + (long long)g * batch * nn;
+        CKI(c.gemm(c.w.M, OP_N, Bg, nn, OP_N, RL, nn, nullptr, SCALE_NONE, sw.Rd, SCALE_MUL));   // (U Lv) Dv   (:133-135)
+        CKI(c.ldr(RL, sw.Rd, c.w.Mp, c.w.M, nn));                                                // ldr!        (:138)
+        CKI(c.gemm(RR2, OP_N, c.w.Mp, nn, OP_N, RR, nn));                                        // R0 Rv       (:141)
+        { T* t = RR; RR = RR2; RR2 = t; }
+        CKI(inv_IpUV_impl<T>(h, n, batch, Gs, RL, sw.Rd, RR, sw.sl(g + 1, n, batch), sw.sd(g + 1, n, batch),
+                             sw.sr(g + 1, n, batch), logdet + (size_t)(g + 1) * batch, sign + (size_t)(g + 1) * batch, sw.ws));
+        if (dG) CK(maxabsdiff_batched<T>(dG + (size_t)g * batch, Gs, Gw, nn, nn, batch, s));
+        { T* t = Gw; Gw = Gs; Gs = t; }
+    }
+    return c.copy(G, Gw);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1074,6 +1208,33 @@ int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L, int n_s
                                          logdet, (double*)sign, (double*)Lout, dout, (double*)Rout, ws, ws_bytes);
     return greens_chain_impl<cplx>(h, n, batch, L, n_stab, (const cplx*)expK, fields, lam, inverse, (cplx*)G, logdet,
                                    (cplx*)sign, (cplx*)Lout, dout, (cplx*)Rout, ws, ws_bytes);
+}
+
+size_t sla_sweep_workspace_bytes(int dtype, int n, int batch, int L, int n_stab) {
+    if (n <= 0 || batch <= 0 || L <= 0 || n_stab <= 0 || L % n_stab) return 0;
+    if ((dtype != SLA_F64 && dtype != SLA_C64) || !n_supported(dtype, n)) return 0;
+    return dtype == SLA_F64 ? SweepWs<double>::bytes(n, batch, L, n_stab) : SweepWs<cplx>::bytes(n, batch, L, n_stab);
+}
+
+int* sla_sweep_workspace_info(void* ws, int dtype, int n, int batch, int L, int n_stab) {
+    if (!ws || n <= 0 || batch <= 0 || L <= 0 || n_stab <= 0 || L % n_stab) return nullptr;
+    if (dtype == SLA_F64) return Ws<double>(SweepWs<double>(ws, n, batch, L, n_stab).ws, n, batch).info;
+    return Ws<cplx>(SweepWs<cplx>(ws, n, batch, L, n_stab).ws, n, batch).info;
+}
+
+int sla_sweep(sla_handle_t h, int dtype, int n, int batch, int L, int n_stab, const void* expK, const void* expKinv,
+              const signed char* fields, double lam, void* G0, void* G, double* logdet, void* sign, double* dG, void* ws,
+              size_t ws_bytes) {
+    CHECK_COMMON(h, dtype, n, batch);
+    if (L <= 0) return -5;
+    if (n_stab <= 0 || L % n_stab) return -6;
+    if (!expK) return -7; if (!expKinv) return -8; if (!fields) return -9;
+    if (!G) return -12; if (!logdet) return -13; if (!sign) return -14; if (!ws) return -16;
+    if (dtype == SLA_F64)
+        return sweep_impl<double>(h, n, batch, L, n_stab, (const double*)expK, (const double*)expKinv, fields, lam,
+                                  (double*)G0, (double*)G, logdet, (double*)sign, dG, ws, ws_bytes);
+    return sweep_impl<cplx>(h, n, batch, L, n_stab, (const cplx*)expK, (const cplx*)expKinv, fields, lam, (cplx*)G0,
+                            (cplx*)G, logdet, (cplx*)sign, dG, ws, ws_bytes);
 }
 
 }  // extern "C"

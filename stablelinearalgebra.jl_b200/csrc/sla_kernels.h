@@ -84,6 +84,8 @@ template <typename T> struct CombineArgs {
 template <typename T> cudaError_t combine_batched(const CombineArgs<T>& a, cudaStream_t s);
 // out4 = [sum logdet, sum Re sign, sum Im sign, batch] (local part of the cross-walker all-reduce)
 template <typename T> cudaError_t walker_sums_batched(double* out4, const double* logdet, const T* sign, int batch, cudaStream_t s);
+// out[b] = max |A[b] - B[b]| over the nn elements of matrix b (NaN if any difference is NaN)
+template <typename T> cudaError_t maxabsdiff_batched(double* out, const T* A, const T* B, long long nn, long long stride, int batch, cudaStream_t s);
 // out[i] = multiplier realising ScaleMode `mode` with d[i] (feeds the GEMM epilogue, which only multiplies)
 cudaError_t scale_prep_batched(double* out, const double* d, int mode, long long count, cudaStream_t s);
 // ev[c,l,i] = exp(lam * s[c,l,i])

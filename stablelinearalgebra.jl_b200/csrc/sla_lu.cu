@@ -8,10 +8,13 @@
 // U12 comes from a register-resident forward substitution and the rank-NB trailing update runs on
 // DMMA from the shared panels.  The inverse is formed as X = U^-1 (L^-1 P) by two blocked triangular
 // sweeps built from the same pieces (mathematically the same inverse ?getri returns).
+#include <cooperative_groups.h>
 #include <cstdio>
 
 #include "sla_cta.cuh"
 #include "sla_kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace sla {
 
@@ -295,10 +298,12 @@ __device__ void lu_logdet(const T* __restrict__ A, int lda, int n, const int* ip
     __syncthreads();
 }
 
-// X = A^-1 * RHS from the LU factors (RHS = identity when rhs == nullptr, i.e. the inverse).
+// X = A^-1 * RHS from the LU factors (RHS = identity when rhs == nullptr, i.e. the inverse), columns [c_lo, c_hi) of X
+// only: the columns of X are independent, so the CTAs of a cluster split them (see lu_kernel).
 template <typename T, int NB>
 __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restrict__ X, int ldx, T* Ps, T* Us,
-                           int ld, const int* ipiv, int* rowpos, const T* __restrict__ rhs, int ldrhs, T* rdiag) {
+                           int ld, const int* ipiv, int* rowpos, const T* __restrict__ rhs, int ldrhs, T* rdiag,
+                           int c_lo, int c_hi) {
     const int tid = threadIdx.x;
     // X = P (row-permuted identity): row r of P*I is e_{src(r)}
     for (int r = tid; r < n; r += CTA_THREADS) rowpos[r] = r;
@@ -309,7 +314,7 @@ __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restric
             if (pk != k) { int t = rowpos[k]; rowpos[k] = rowpos[pk]; rowpos[pk] = t; }
         }
     __syncthreads();
-    for (int c = tid >> 5; c < n; c += CTA_WARPS)
+    for (int c = c_lo + (tid >> 5); c < c_hi; c += CTA_WARPS)
         for (int r = (tid & 31); r < n; r += 32)
             X[(long long)c * ldx + r] = rhs ? rhs[(long long)c * ldrhs + rowpos[r]] : mk<T>(rowpos[r] == c ? 1.0 : 0.0);
     __syncthreads();
@@ -320,7 +325,7 @@ __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restric
             for (int r = tid; r < n; r += CTA_THREADS)
                 Ps[(size_t)i * ld + r] = (i < jb && r > p0 + i) ? A[(long long)(p0 + i) * lda + r] : mk<T>(0.0);
         __syncthreads();
-        for (int c = tid; c < n; c += CTA_THREADS) {
+        for (int c = c_lo + tid; c < c_hi; c += CTA_THREADS) {
             T a[NB];
             T* col = X + (long long)c * ldx + p0;
 #pragma unroll
@@ -339,7 +344,7 @@ __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restric
             }
         }
         __syncthreads();
-        cta_rank_update<T, false>(X, ldx, kend, n, 0, n, Ps, Us, ld, jb, n - 1);
+        cta_rank_update<T, false>(X, ldx, kend, n, c_lo, c_hi, Ps, Us, ld, jb, n - 1);
         __syncthreads();
     }
     // ---- backward sweep: X = U^-1 Y
@@ -353,7 +358,7 @@ __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restric
         // reciprocals of the panel's diagonal, once per panel (the substitution below multiplies)
         if (tid < jb) rdiag[tid] = mk<T>(1.0) / Ps[(size_t)tid * ld + p0 + tid];
         __syncthreads();
-        for (int c = tid; c < n; c += CTA_THREADS) {
+        for (int c = c_lo + tid; c < c_hi; c += CTA_THREADS) {
             T a[NB];
             T* col = X + (long long)c * ldx + p0;
 #pragma unroll
@@ -374,15 +379,20 @@ __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restric
             }
         }
         __syncthreads();
-        cta_rank_update<T, false>(X, ldx, 0, p0, 0, n, Ps, Us, ld, jb, n - 1);
+        cta_rank_update<T, false>(X, ldx, 0, p0, c_lo, c_hi, Ps, Us, ld, jb, n - 1);
         __syncthreads();
     }
 }
 
+// One matrix per CTA, or per CLUSTER of CS CTAs: the factorisation (pivot search = a serial chain) runs in CTA 0; the
+// two triangular sweeps that form X = U^-1 L^-1 P -- 3/4 of the flops of an inverse -- are independent per column of X, so
+// the cluster splits the columns.  Small batches (64 matrices on 148 SMs) otherwise leave more than half of the GPU idle.
 template <typename T, int NB>
 __global__ void __launch_bounds__(CTA_THREADS, 1) lu_kernel(LuArgs<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = p.n, b = blockIdx.x, tid = threadIdx.x;
+    cg::cluster_group cl = cg::this_cluster();
+    const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int n = p.n, b = blockIdx.x / CS, tid = threadIdx.x;
     const int ld = panel_ld<T>(n);
     T* Ps = reinterpret_cast<T*>(smem_raw);
     T* Us = Ps + (size_t)NB * ld;
@@ -399,33 +409,65 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) lu_kernel(LuArgs<T> p) {
     // info is cleared once per C-API entry point (sla_capi.cu: clear_info), not per kernel: composite calls run two or
     // three LU factorisations and the FIRST failure has to survive (the reference throws at every getrf!, lu.jl:75)
     int* info = p.info ? p.info + b : nullptr;
-    lu_factor<T, NB>(A, p.lda, n, Ps, Us, ld, ipiv, rowpos, tl, tsrc, redv, redi, misc, info);
-    double logdet; T sgn;
-    lu_logdet<T>(A, p.lda, n, ipiv, redv, redt, logdet, sgn);
-    if (p.ipiv_out)
-        for (int i = tid; i < n; i += CTA_THREADS) p.ipiv_out[(long long)b * n + i] = ipiv[i] + 1;
+    double logdet = 0.0; T sgn = mk<T>(1.0);
+    if (rank == 0) {
+        lu_factor<T, NB>(A, p.lda, n, Ps, Us, ld, ipiv, rowpos, tl, tsrc, redv, redi, misc, info);
+        lu_logdet<T>(A, p.lda, n, ipiv, redv, redt, logdet, sgn);
+        if (p.ipiv_out)
+            for (int i = tid; i < n; i += CTA_THREADS) p.ipiv_out[(long long)b * n + i] = ipiv[i] + 1;
+    }
+    if (CS > 1) {
+        __threadfence();   // the factors in global memory are read by the peers after the barrier
+        cl.sync();
+        if (rank != 0) {
+            const int* rip = cl.map_shared_rank(ipiv, 0);
+            for (int i = tid; i < n; i += CTA_THREADS) ipiv[i] = rip[i];
+        }
+        cl.sync();         // CTA 0 may reuse / leave its shared memory only after the peers have copied the pivots
+    }
     if (p.invert) {
+        // column slice of this CTA (multiples of the 32-column warp tile of cta_rank_update)
+        const int per = (((n + CS - 1) / CS) + 31) & ~31;
+        const int c_lo = min(n, rank * per), c_hi = min(n, c_lo + per);
         T* X = p.X + (long long)b * p.strideX;
         T* rhs = p.rhs ? p.rhs + (long long)b * p.strideRhs : nullptr;
-        lu_inverse<T, NB>(A, p.lda, n, X, p.ldx, Ps, Us, ld, ipiv, rowpos, rhs, p.ldrhs, redt);
+        lu_inverse<T, NB>(A, p.lda, n, X, p.ldx, Ps, Us, ld, ipiv, rowpos, rhs, p.ldrhs, redt, c_lo, c_hi);
         if (rhs) {   // ldiv_lu!: the solution replaces the right-hand side (src/lu.jl:167-176)
             __syncthreads();
-            for (int c = tid >> 5; c < n; c += CTA_WARPS)
+            for (int c = c_lo + (tid >> 5); c < c_hi; c += CTA_WARPS)
                 for (int r = (tid & 31); r < n; r += 32) rhs[(long long)c * p.ldrhs + r] = X[(long long)c * p.ldx + r];
         } else if (p.copy_back) {
-            for (int c = tid >> 5; c < n; c += CTA_WARPS)
+            if (CS > 1) cl.sync();   // every CTA has finished reading the factors that A^-1 now overwrites
+            for (int c = c_lo + (tid >> 5); c < c_hi; c += CTA_WARPS)
                 for (int r = (tid & 31); r < n; r += 32) A[(long long)c * p.lda + r] = X[(long long)c * p.ldx + r];
         }
         logdet = -logdet;      // src/lu.jl:157
         sgn = conj_(sgn);
     }
-    if (tid == 0) {
+    if (tid == 0 && rank == 0) {
         if (p.logdet) p.logdet[b] = logdet;
         if (p.sign) p.sign[b] = sgn;
     }
 }
 
 }  // namespace
+
+// cluster size of the inverse: as many CTAs per matrix as keep the whole batch in ONE wave (SLA_LU_CLUSTER overrides)
+static int lu_cluster_size(int n, int batch, int invert) {
+    static const int forced = getenv("SLA_LU_CLUSTER") ? atoi(getenv("SLA_LU_CLUSTER")) : 0;
+    if (!invert) return 1;
+    if (forced == 1 || forced == 2 || forced == 4) return forced;
+    static int sms[kMaxDevices] = {};
+    const int dev = current_device();
+    int nsm = 148;
+    if (dev >= 0 && dev < kMaxDevices) {
+        if (sms[dev] == 0 && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms[dev] = 148;
+        nsm = sms[dev];
+    }
+    if (n >= 512 && (long long)batch * 4 <= nsm) return 4;
+    if (n >= 128 && (long long)batch * 2 <= nsm) return 2;
+    return 1;
+}
 
 template <typename T> cudaError_t lu_batched(const LuArgs<T>& p, cudaStream_t stream) {
     if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
@@ -434,12 +476,25 @@ template <typename T> cudaError_t lu_batched(const LuArgs<T>& p, cudaStream_t st
     while (nb >= 8 && lu_smem_bytes<T>(p.n, nb) > limit) nb >>= 1;
     if (nb < 8) return cudaErrorInvalidValue;
     size_t smem = lu_smem_bytes<T>(p.n, nb);
+    const int cs = lu_cluster_size(p.n, p.batch, p.invert);
     auto launch = [&](auto kern) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<p.batch, CTA_THREADS, smem, stream>>>(p);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)p.batch * cs, 1, 1);
+        cfg.blockDim = dim3(CTA_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = cs > 1 ? 1 : 0;
+        e = cudaLaunchKernelEx(&cfg, kern, p);
         ++g_launch_count;
-        return cudaGetLastError();
+        return e != cudaSuccess ? e : cudaGetLastError();
     };
     if (nb == 32) return launch(lu_kernel<T, 32>);
     if (nb == 16) return launch(lu_kernel<T, 16>);

@@ -244,6 +244,37 @@ cudaError_t hs_exp_batched(double* ev, const signed char* fields, double lam, lo
     return cudaGetLastError();
 }
 
+// out[b] = max_ij |A[b](i,j) - B[b](i,j)|: the wrap error a DQMC sweep monitors at every re-stabilisation (sla_sweep).
+// One CTA per matrix; NaNs propagate (fmax would drop them) so that a broken propagation cannot hide.
+template <typename T> __global__ void maxabsdiff_kernel(double* out, const T* A, const T* B, long long nn, long long stride) {
+    __shared__ double red[8];
+    __shared__ int bad[8];
+    const T* a = A + (long long)blockIdx.x * stride;
+    const T* b = B + (long long)blockIdx.x * stride;
+    double m = 0.0;
+    int nanf = 0;
+    for (long long i = threadIdx.x; i < nn; i += blockDim.x) {
+        const double v = abs_(a[i] - b[i]);
+        nanf |= !(v == v);
+        m = fmax(m, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) { m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o)); nanf |= __shfl_xor_sync(0xffffffffu, nanf, o); }
+    if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = m; bad[threadIdx.x >> 5] = nanf; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { m = fmax(m, red[w]); nanf |= bad[w]; }
+        out[blockIdx.x] = nanf ? nan("") : m;
+    }
+}
+template <typename T> cudaError_t maxabsdiff_batched(double* out, const T* A, const T* B, long long nn, long long stride, int batch, cudaStream_t s) {
+    if (batch <= 0) return cudaSuccess;
+    maxabsdiff_kernel<T><<<batch, 256, 0, s>>>(out, A, B, nn, stride);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+template cudaError_t maxabsdiff_batched<double>(double*, const double*, const double*, long long, long long, int, cudaStream_t);
+template cudaError_t maxabsdiff_batched<cplx>(double*, const cplx*, const cplx*, long long, long long, int, cudaStream_t);
+
 template <typename T> cudaError_t walker_sums_batched(double* out4, const double* logdet, const T* sign, int batch, cudaStream_t s) {
     walker_sums_kernel<T><<<1, 256, 0, s>>>(out4, logdet, sign, batch);
     ++g_launch_count;

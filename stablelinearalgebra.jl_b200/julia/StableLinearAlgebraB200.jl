@@ -5,8 +5,8 @@
 # `ldrs!(Fs, A::AbstractArray{T,3}, ws)`, src/LDR.jl:249-257): every method body is ONE ccall.
 #
 # NOTE: Julia is not installed in the build image, so this file is shipped as source and has not been
-# executed there; the identical C symbols are exercised from Python (tests/test_gpu_parity.py), which
-# leaves only the marshalling below untested.
+# executed there; the identical C symbols are exercised from Python (tests/test_gpu_parity.py) and, with exactly the
+# argument types of the ccall tuples below, from a plain-C client (tests/abi_c/abi_check.c).
 module StableLinearAlgebraB200
 
 using CUDA
@@ -15,7 +15,7 @@ import LinearAlgebra: adjoint!, lmul!, rmul!, mul!, ldiv!, rdiv!, logabsdet
 import Base: eltype, size, copyto!
 
 export LDR, LDRWorkspace, ldr, ldr!, ldrs, ldrs!, ldr_workspace
-export inv_IpA!, inv_IpUV!, inv_UpV!, inv_invUpV!, inv_lu!, det_lu!, ldiv_lu!, greens_chain!
+export inv_IpA!, inv_IpUV!, inv_UpV!, inv_invUpV!, inv_lu!, det_lu!, ldiv_lu!, greens_chain!, sweep!
 
 const libsla = get(ENV, "LIBSLA_B200", "libsla_b200.so")
 const SLA_F64, SLA_C64 = Cint(0), Cint(1)
@@ -33,8 +33,13 @@ function Handle()
     finalizer(x -> ccall((:sla_destroy, libsla), Cint, (Ptr{Cvoid},), x.ptr), h)
     return h
 end
-const HANDLE = Ref{Union{Nothing,Handle}}(nothing)
-handle() = (HANDLE[] === nothing && (HANDLE[] = Handle()); HANDLE[].ptr)
+# CUDA.jl gives every task its own stream: one library handle per task (task_local_storage), re-bound to the task's
+# CURRENT stream before every call, so that library kernels are ordered with the surrounding CuArray operations.
+function handle()
+    h = get!(() -> Handle(), task_local_storage(), :sla_b200_handle)::Handle
+    chk(ccall((:sla_set_stream, libsla), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h.ptr, CUDA.stream().handle), "sla_set_stream")
+    return h.ptr
+end
 
 function chk(code::Cint, what)
     code == 0 && return nothing
@@ -232,18 +237,75 @@ for (jl, sym) in ((:inv_IpUV!, :sla_inv_IpUV), (:inv_UpV!, :sla_inv_UpV), (:inv_
     end
 end
 
+# ---- source compatibility with the reference's single-matrix signatures -----------------------------------------
+# `ldr(A::CuMatrix)` is a batch of one (L, R of size (n, n, 1)); the inverses / determinants called with a CuMatrix
+# return the reference's `Tuple{E,T}` of host scalars (src/exported_functions.jl:25, src/lu.jl:123,149) instead of
+# device vectors.
+as3(A::CuArray{T,2}) where {T} = reshape(A, size(A, 1), size(A, 2), 1)
+first_scalar(ld, sg) = (Array(ld)[1], Array(sg)[1])
+ldr_workspace(A::CuArray{T,2}) where {T<:BlasT} = ldr_workspace(as3(A))
+ldr(A::CuArray{T,2}) where {T<:BlasT} = ldr(as3(A))
+ldr(A::CuArray{T,2}, ws::LDRWorkspace{T}) where {T<:BlasT} = ldr(as3(A), ws)
+copyto!(U::CuArray{T,2}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = (copyto!(as3(U), V, ws); U)
+adjoint!(U::CuArray{T,2}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = (adjoint!(as3(U), V, ws); U)
+lmul!(U::LDR{T}, V::CuArray{T,2}, ws::LDRWorkspace{T}) where {T} = (lmul!(U, as3(V), ws); V)
+rmul!(U::CuArray{T,2}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = (rmul!(as3(U), V, ws); U)
+ldiv!(U::LDR{T}, V::CuArray{T,2}, ws::LDRWorkspace{T}) where {T} = (ldiv!(U, as3(V), ws); V)
+rdiv!(U::CuArray{T,2}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = (rdiv!(as3(U), V, ws); U)
+det_lu!(A::CuArray{T,2}, ws::LDRWorkspace{T}) where {T} = first_scalar(det_lu!(as3(A), ws)...)
+inv_lu!(A::CuArray{T,2}, ws::LDRWorkspace{T}) where {T} = first_scalar(inv_lu!(as3(A), ws)...)
+ldiv_lu!(A::CuArray{T,2}, B::CuArray{T,2}, ws::LDRWorkspace{T}) where {T} = first_scalar(ldiv_lu!(as3(A), as3(B), ws)...)
+inv_IpA!(G::CuArray{T,2}, A::LDR{T}, ws::LDRWorkspace{T}) where {T} = first_scalar(inv_IpA!(as3(G), A, ws)...)
+inv_IpUV!(G::CuArray{T,2}, U::LDR{T}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = first_scalar(inv_IpUV!(as3(G), U, V, ws)...)
+inv_UpV!(G::CuArray{T,2}, U::LDR{T}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = first_scalar(inv_UpV!(as3(G), U, V, ws)...)
+inv_invUpV!(G::CuArray{T,2}, U::LDR{T}, V::LDR{T}, ws::LDRWorkspace{T}) where {T} = first_scalar(inv_invUpV!(as3(G), U, V, ws)...)
+
+# ---- fused drivers: their workspace blobs are cached per (entry point, eltype, sizes) and task -------------------------
+function driver_blob(key, bytes)
+    cache = get!(() -> Dict{Any,CuArray{UInt8,1}}(), task_local_storage(), :sla_b200_blobs)::Dict{Any,CuArray{UInt8,1}}
+    blob = get(cache, key, nothing)
+    if blob === nothing || length(blob) < bytes
+        blob = CUDA.zeros(UInt8, bytes)
+        cache[key] = blob
+    end
+    return blob
+end
+
 "Fused driver: one stabilised G(0) evaluation per chain (sla_greens_chain); fields is Int8 (n, L, batch)."
 function greens_chain!(G::CuArray{T,3}, expK::CuArray{T,2}, fields::CuArray{Int8,3}, lam::Real, n_stab::Integer;
                        inverse::Symbol = :IpA) where {T<:BlasT}
     n, L, b = size(fields)
     bytes = ccall((:sla_greens_chain_workspace_bytes, libsla), Csize_t, (Cint, Cint, Cint, Cint, Cint), dtype(T), n, b, L, n_stab)
-    ws = CUDA.zeros(UInt8, bytes)
+    bytes == 0 && throw(ArgumentError("greens_chain!: unsupported sizes (n = $n, L = $L, n_stab = $n_stab)"))
+    ws = driver_blob((:chain, T, n, b, L, n_stab), bytes)
     ld, sg = scalars(T, b)
     chk(ccall((:sla_greens_chain, libsla), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, CuPtr{Cvoid}, CuPtr{Int8}, Cdouble,
               Cint, CuPtr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cvoid}, CuPtr{Cvoid}, Csize_t),
               handle(), dtype(T), n, b, L, n_stab, expK, fields, Float64(lam), inverse === :IpA ? 0 : 1, G, ld, sg,
               CU_NULL, CU_NULL, CU_NULL, ws, bytes), "sla_greens_chain")
     return ld, sg
+end
+
+"""
+Fused sweep stepper (sla_sweep): stack of left factorisations by `rmul!`, G(0) by `inv_IpA!`, then per slice
+G <- B_l G B_l^-1 and every n_stab slices `lmul!` + `inv_IpUV!(G, F_right, F_left[g])`.  Returns
+(logdet (batch, ng+1), sign (batch, ng+1), dG (batch, ng)); G receives G(beta), G0 (optional) G(0).
+"""
+function sweep!(G::CuArray{T,3}, expK::CuArray{T,2}, expKinv::CuArray{T,2}, fields::CuArray{Int8,3}, lam::Real,
+                n_stab::Integer; G0::Union{Nothing,CuArray{T,3}} = nothing) where {T<:BlasT}
+    n, L, b = size(fields)
+    ng = L ÷ n_stab
+    bytes = ccall((:sla_sweep_workspace_bytes, libsla), Csize_t, (Cint, Cint, Cint, Cint, Cint), dtype(T), n, b, L, n_stab)
+    bytes == 0 && throw(ArgumentError("sweep!: unsupported sizes (n = $n, L = $L, n_stab = $n_stab)"))
+    ws = driver_blob((:sweep, T, n, b, L, n_stab), bytes)
+    ld = CuArray{Float64}(undef, b, ng + 1)
+    sg = CuArray{T}(undef, b, ng + 1)
+    dG = CuArray{Float64}(undef, b, ng)
+    chk(ccall((:sla_sweep, libsla), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Cint, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Int8},
+              Cdouble, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cvoid}, Csize_t),
+              handle(), dtype(T), n, b, L, n_stab, expK, expKinv, fields, Float64(lam), G0 === nothing ? CU_NULL : G0, G, ld, sg,
+              dG, ws, bytes), "sla_sweep")
+    return ld, sg, dG
 end
 
 end # module

@@ -238,3 +238,27 @@ def test_mul_wrappers(S):
         O.mul_(HF, U, V, S.ws)
         O.copyto_(A, HF, S.ws)
         assert approx(A, ref)
+
+
+def test_sweep_oracle_self_consistency():
+    """oracle/sweep.py: without field updates G(beta) = G(0), every re-stabilised G(tau_g) equals the
+    direct evaluation (I + B(tau_g,0) B(beta,tau_g))^-1, log|det| and sign do not depend on tau, wrap errors are noise."""
+    import sla_b200 as sla
+    from oracle import chain as ochain
+    from oracle import sweep as osweep
+    cfg = sla.synthetic.HubbardConfig("t", 4, 40, 5, 1)
+    expK = cfg.expK()
+    expKinv = np.linalg.inv(expK)
+    f = cfg.fields([3])[0]
+    r = osweep.sweep(expK, expKinv, f, cfg.lam, cfg.n_stab)
+    G_direct, ld, sg, _ = ochain.eval_greens(expK, f, cfg.lam, cfg.n_stab, "IpA")
+    assert np.max(np.abs(r["G0"] - G_direct)) < 1e-12
+    assert np.max(np.abs(r["G"] - r["G0"])) < 1e-11
+    assert np.allclose(r["logdet"], ld, rtol=0, atol=1e-9) and abs(r["logdet0"] - ld) < 1e-10
+    assert np.all(r["sign"] == sg) and r["sign0"] == sg
+    assert np.all(r["dG"] < 1e-10)
+    # G(tau_2) directly: cyclic shift of the slices by two groups
+    shift = 2 * cfg.n_stab
+    G2, _, _, _ = ochain.eval_greens(expK, np.concatenate([f[shift:], f[:shift]]), cfg.lam, cfg.n_stab, "IpA")
+    r2 = osweep.sweep(expK, expKinv, np.concatenate([f[shift:], f[:shift]]), cfg.lam, cfg.n_stab)
+    assert np.max(np.abs(r2["G0"] - G2)) < 1e-12
