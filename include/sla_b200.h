@@ -11,7 +11,8 @@
  *     mirroring the reference's "no allocations after construction" rule (src/LDR.jl:39).
  *   - matrices: column-major n x n, leading dimension n, batch stride n*n elements (= Julia
  *     CuArray{T,3} of size (n,n,batch));  d: n reals per matrix, batch stride n.
- *   - dtype: SLA_F64 (Float64) or SLA_C64 (ComplexF64, interleaved re,im).  E = Float64 always.
+ *   - dtype: SLA_F64 (Float64) or SLA_C64 (ComplexF64, interleaved re,im); SLA_F32 / SLA_C32 as storage types.
+ *     E = Float64 always.
  *   - logdet: double[batch];  sign: T[batch] (double, or (re,im) pair for SLA_C64) -- the
  *     Tuple{E,T} the reference's inverses return (src/exported_functions.jl:25).
  *   - every call is asynchronous on the handle's stream; a handle is bound to one stream and one
@@ -34,6 +35,12 @@ extern "C" {
 
 #define SLA_F64 0
 #define SLA_C64 1
+/* Float32 / ComplexF32 STORAGE types (src/qr.jl:29-32, src/lu.jl:26-29 generate all four element types): matrices and
+ * signs are float / (float, float) in the caller's buffers; d and log|det| stay double (LDR{Float32,Float64}: a
+ * chain's D leaves the Float32 range); every entry point promotes to FP64 inside the workspace, runs the FP64 kernels
+ * and demotes.  Not supported by sla_gemm and sla_walker_sums (plain Float32 GEMMs are the caller's cuBLAS business). */
+#define SLA_F32 2
+#define SLA_C32 3
 #define SLA_OP_N 0
 #define SLA_OP_C 1 /* conjugate transpose (adjoint) */
 #define SLA_INV_IPA 0
@@ -47,6 +54,7 @@ extern "C" {
 #define SLA_LDR_ALGO_STREAMING 3 /* one CTA per matrix, L2-streaming (csrc/sla_ldr.cu) */
 #define SLA_LDR_ALGO_HYBRID 4    /* registers + shared memory, clusters of 2 (csrc/sla_ldr_reg.cu) */
 #define SLA_LDR_ALGO_BLOCKED 5   /* blocked panel + tensor-core trailing update (csrc/sla_ldr_blk.cu) */
+#define SLA_LDR_ALGO_MULTICTA 6  /* L2-streaming, a cluster of 2-8 CTAs per matrix (csrc/sla_ldr_mc.cu) */
 /* per-matrix info codes (sla_workspace_info): k > 0 = U(k,k) exactly zero or not finite in an LU (src/lu.jl:75,91);
  * SLA_INFO_RANGE = a column norm of an ldr! input left the range in which squared norms are representable */
 #define SLA_INFO_RANGE (-1)

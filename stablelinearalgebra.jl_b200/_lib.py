@@ -12,12 +12,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # SLA_B200_LIB: another build of the same library (kernel A/B experiments under profiles/); never a fallback
 LIB_PATH = os.environ.get("SLA_B200_LIB") or os.path.join(HERE, "csrc", "libsla_b200.so")
 
-SLA_F64, SLA_C64 = 0, 1
+SLA_F64, SLA_C64, SLA_F32, SLA_C32 = 0, 1, 2, 3
 SLA_OP_N, SLA_OP_C = 0, 1
 SLA_INV_IPA, SLA_INV_IPUV = 0, 1
 SLA_ENOTIMPL, SLA_EDEVICE = -100, -101
 SLA_INFO_RANGE = -1
-LDR_ALGOS = {0: "none", 1: "reg", 2: "cluster", 3: "streaming", 4: "hybrid", 5: "blocked"}
+LDR_ALGOS = {0: "none", 1: "reg", 2: "cluster", 3: "streaming", 4: "hybrid", 5: "blocked", 6: "multicta"}
 
 _vp, _i, _ll, _sz, _dbl = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_double
 _common = [_vp, _i, _i, _i]  # handle, dtype, n, batch

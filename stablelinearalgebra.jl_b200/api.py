@@ -33,12 +33,21 @@ class SlaError(RuntimeError):
     pass
 
 
+_CODES = {torch.float64: _lib.SLA_F64, torch.complex128: _lib.SLA_C64, torch.float32: _lib.SLA_F32,
+          torch.complex64: _lib.SLA_C32}
+
+
+def _code_of(dtype: torch.dtype) -> int:
+    """Element-type code of the C ABI.  Float32 / ComplexF32 are storage types (promoted to FP64 inside the library;
+    ``d`` and ``log|det|`` stay Float64, see include/sla_b200.h)."""
+    try:
+        return _CODES[dtype]
+    except KeyError:
+        raise TypeError(f"unsupported element type {dtype} (Float64 / ComplexF64 / Float32 / ComplexF32)") from None
+
+
 def _dtype_code(t: torch.Tensor) -> int:
-    if t.dtype == torch.float64:
-        return _lib.SLA_F64
-    if t.dtype == torch.complex128:
-        return _lib.SLA_C64
-    raise TypeError(f"unsupported element type {t.dtype} (Float64 / ComplexF64 only)")
+    return _code_of(t.dtype)
 
 
 def _check(code: int, what: str):
@@ -88,7 +97,10 @@ def to_device(A, device="cuda") -> torch.Tensor:
     A = np.asarray(A)
     if A.ndim == 2:
         A = A[None]
-    dt = np.complex128 if np.iscomplexobj(A) else np.float64
+    if A.dtype in (np.float32, np.complex64):
+        dt = A.dtype                       # Float32 / ComplexF32 storage types are kept
+    else:
+        dt = np.complex128 if np.iscomplexobj(A) else np.float64
     At = np.ascontiguousarray(np.swapaxes(A.astype(dt, copy=False), 1, 2))
     return torch.from_numpy(At).to(device)
 
@@ -129,7 +141,7 @@ class LDRWorkspace:
     def __init__(self, n: int, batch: int, dtype: torch.dtype, device="cuda"):
         lib = _lib.load()
         self.n, self.batch, self.dtype = n, batch, dtype
-        self.code = _lib.SLA_F64 if dtype == torch.float64 else _lib.SLA_C64
+        self.code = _code_of(dtype)
         self.nbytes = lib.sla_workspace_bytes(self.code, n, batch)
         if self.nbytes == 0:
             raise SlaError(f"unsupported size n={n} (1 <= n <= {lib.sla_max_n(self.code)} for this element type) or "
@@ -163,7 +175,7 @@ def check_info(ws: LDRWorkspace):
 def greens_chain_info(ws: torch.Tensor, dtype: torch.dtype, n: int, batch: int, L: int, n_stab: int) -> torch.Tensor:
     """The per-chain info codes inside a ``greens_chain`` workspace blob (same meaning as ``LDRWorkspace.info``)."""
     lib = _lib.load()
-    code = _lib.SLA_F64 if dtype == torch.float64 else _lib.SLA_C64
+    code = _code_of(dtype)
     p = lib.sla_greens_chain_workspace_info(C.c_void_p(ws.data_ptr()), code, n, batch, L, n_stab)
     off = p - ws.data_ptr()
     return ws[off:off + 4 * batch].view(torch.int32)
@@ -526,7 +538,7 @@ def walker_sums(logdet: torch.Tensor, sign: torch.Tensor, out: torch.Tensor | No
 
 def greens_chain_workspace_bytes(dtype: torch.dtype, n: int, batch: int, L: int, n_stab: int) -> int:
     lib = _lib.load()
-    code = _lib.SLA_F64 if dtype == torch.float64 else _lib.SLA_C64
+    code = _code_of(dtype)
     return lib.sla_greens_chain_workspace_bytes(code, n, batch, L, n_stab)
 
 
@@ -600,7 +612,7 @@ def sweep(expK, expKinv, fields, lam: float, n_stab: int, G=None, G0=None, logde
 def sweep_info(ws: torch.Tensor, dtype: torch.dtype, n: int, batch: int, L: int, n_stab: int) -> torch.Tensor:
     """The per-chain info codes inside a ``sweep`` workspace blob (same meaning as ``LDRWorkspace.info``)."""
     lib = _lib.load()
-    code = _lib.SLA_F64 if dtype == torch.float64 else _lib.SLA_C64
+    code = _code_of(dtype)
     p = lib.sla_sweep_workspace_info(C.c_void_p(ws.data_ptr()), code, n, batch, L, n_stab)
     off = p - ws.data_ptr()
     return ws[off:off + 4 * batch].view(torch.int32)

@@ -7,6 +7,7 @@
 #include <new>
 
 #include "../../include/sla_b200.h"
+#include "sla_capi_f32.h"
 #include "sla_kernels.h"
 
 using namespace sla;
@@ -129,6 +130,7 @@ template <typename T> struct Ctx {
         a.d = d; a.stride_d = n;
         a.R = Rout; a.strideR = nn; a.ldr = n;
         a.Twork = w.Tw; a.strideT = (long long)w.tw_elems;
+        a.Qwork = w.X; a.strideQ = nn;   // X is the LU scratch: free during every factorisation
         a.jpvt_out = nullptr;
         a.prof = g_ldr_prof;
         a.n = n; a.batch = batch;
@@ -138,7 +140,7 @@ template <typename T> struct Ctx {
             const char* e = getenv("SLA_LDR_ALGO");
             if (getenv("SLA_LDR_STREAMING")) return 3;
             if (!e) return 0;
-            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : (e[0] == 'h' ? 4 : (e[0] == 'b' ? 5 : 0))));
+            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : (e[0] == 'h' ? 4 : (e[0] == 'b' ? 5 : (e[0] == 'm' ? 6 : 0)))));
         }();
         // Cluster kernels minimise latency (one matrix per CS SMs, ~132/CS matrices in flight), the streaming
         // kernel maximises throughput (one matrix per SM, 148 in flight) but is ~4x (register kernel) / ~2.5x
@@ -167,8 +169,22 @@ template <typename T> struct Ctx {
         // panel update lengthens the one-warp candidate chain) -- opt-in: SLA_LDR_BLK=1 or SLA_LDR_ALGO=blk
         static const bool blk_on = getenv("SLA_LDR_BLK") && atoi(getenv("SLA_LDR_BLK")) != 0;
         const int cs_blk = ldr_blk_cluster_size<T>(n);
+        // n > 512 (no on-chip kernel) and a batch that leaves SMs idle with one CTA per matrix: the multi-CTA streaming
+        // kernel with as many CTAs per matrix as keep the batch in one wave (clusters of 8 / 4 / 2: ~14 / 33 / 66 resident;
+        // SLA_LDR_MC=0 switches it off, SLA_LDR_ALGO=mc forces it with SLA_LDR_MC_CS CTAs, default 4)
+        static const bool mc_on = !(getenv("SLA_LDR_MC") && atoi(getenv("SLA_LDR_MC")) == 0);
+        static const int mc_forced_cs = getenv("SLA_LDR_MC_CS") ? atoi(getenv("SLA_LDR_MC_CS")) : 0;
+        int cs_mc = 0;
+        if (ldr_mc_supported<T>(n)) {
+            if (batch <= 14) cs_mc = 8;
+            else if (batch <= 33) cs_mc = 4;
+            else if (batch <= 66) cs_mc = 2;
+            if (forced == 6) cs_mc = (mc_forced_cs == 2 || mc_forced_cs == 4 || mc_forced_cs == 8) ? mc_forced_cs : 4;
+        }
         int algo;
-        if (forced == 5) { if (cs_blk == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_BLOCKED; }
+        if (forced == 6) { if (cs_mc == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_MULTICTA; }
+        else if (forced == 0 && mc_on && n > 512 && cs_mc > 0) algo = SLA_LDR_ALGO_MULTICTA;
+        else if (forced == 5) { if (cs_blk == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_BLOCKED; }
         else if (forced == 0 && blk_on && cs_blk > 0) algo = SLA_LDR_ALGO_BLOCKED;
         else if (forced == 4) { if (cs_hyb == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_HYBRID; }
         else if (forced == 1) { if (cs_reg == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_REG; }
@@ -180,6 +196,7 @@ template <typename T> struct Ctx {
         else algo = SLA_LDR_ALGO_STREAMING;
         a.info = w.info;
         switch (algo) {
+            case SLA_LDR_ALGO_MULTICTA: CK(ldr_mc_batched<T>(a, cs_mc, s)); break;
             case SLA_LDR_ALGO_BLOCKED: CK(ldr_blk_batched<T>(a, s)); break;
             case SLA_LDR_ALGO_HYBRID: CK(ldr_hyb_batched<T>(a, s)); break;
             case SLA_LDR_ALGO_REG: CK(ldr_reg_batched<T>(a, s)); break;
@@ -862,9 +879,13 @@ static inline int clear_info(sla_handle_t h, int dtype, int n, int batch, void* 
 #define DISPATCH(dtype, fn, ...) \
     ((dtype) == SLA_F64 ? fn<double>(__VA_ARGS__) : fn<cplx>(__VA_ARGS__))
 
+// SLA_F32 / SLA_C32 are storage types served by promote -> FP64 entry point -> demote (sla_capi_f32.cu)
+static inline bool is_f32(int dtype) { return dtype == SLA_F32 || dtype == SLA_C32; }
+cudaStream_t sla_handle_stream(sla_handle_t h) { return h->stream; }
+
 extern "C" {
 
-int sla_version(void) { return 100; }
+int sla_version(void) { return 101; }
 
 unsigned long long sla_launch_count(void) { return g_launch_count.load(); }
 
@@ -905,6 +926,7 @@ int sla_set_stream(sla_handle_t handle, void* stream) {
 }
 
 int sla_max_n(int dtype) {
+    if (is_f32(dtype)) dtype -= 2;   // storage types compute in FP64
     if (dtype != SLA_F64 && dtype != SLA_C64) return 0;
     int lo = 1, hi = 1 << 14;   // n_supported is monotone in n
     while (lo < hi) { int mid = (lo + hi + 1) / 2; if (n_supported(dtype, mid)) lo = mid; else hi = mid - 1; }
@@ -912,11 +934,13 @@ int sla_max_n(int dtype) {
 }
 
 size_t sla_workspace_bytes(int dtype, int n, int batch) {
+    if (is_f32(dtype)) return f32_workspace_bytes(dtype, n, batch);
     if (n <= 0 || batch <= 0 || (dtype != SLA_F64 && dtype != SLA_C64) || !n_supported(dtype, n)) return 0;
     return dtype == SLA_F64 ? Ws<double>::bytes(n, batch) : Ws<cplx>::bytes(n, batch);
 }
 
 int* sla_workspace_info(void* ws, int dtype, int n, int batch) {
+    if (is_f32(dtype)) dtype -= 2;   // the FP64 workspace is the head of the blob
     if (!ws || n <= 0 || batch <= 0) return nullptr;
     return dtype == SLA_F64 ? Ws<double>(ws, n, batch).info : Ws<cplx>(ws, n, batch).info;
 }
@@ -925,6 +949,7 @@ int* sla_workspace_info(void* ws, int dtype, int n, int batch) {
 #define CTP(x) static_cast<const T*>(x)
 
 int sla_ldr(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R, void* ws) {
+    if (is_f32(dtype)) return f32_ldr(h, dtype, n, batch, L, d, R, ws);
     CHECK_COMMON(h, dtype, n, batch);
     if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!ws) return -8; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldr_impl<double>(h, n, batch, (double*)L, d, (double*)R, ws);
@@ -933,6 +958,7 @@ int sla_ldr(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, voi
 
 int sla_ldr_from(sla_handle_t h, int dtype, int n, int batch, const void* A, long long strideA, void* L, double* d,
                  void* R, void* ws) {
+    if (is_f32(dtype)) return f32_ldr_from(h, dtype, n, batch, A, strideA, L, d, R, ws);
     CHECK_COMMON(h, dtype, n, batch);
     if (!A) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldr_from_impl<double>(h, n, batch, (const double*)A, strideA, (double*)L, d, (double*)R, ws);
@@ -940,6 +966,7 @@ int sla_ldr_from(sla_handle_t h, int dtype, int n, int batch, const void* A, lon
 }
 
 int sla_set_identity(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R) {
+    if (is_f32(dtype)) return f32_set_identity(h, dtype, n, batch, L, d, R);
     CHECK_COMMON(h, dtype, n, batch);
     if (!L) return -5; if (!d) return -6; if (!R) return -7;
     if (dtype == SLA_F64) return set_identity_impl<double>(h, n, batch, (double*)L, d, (double*)R);
@@ -948,6 +975,7 @@ int sla_set_identity(sla_handle_t h, int dtype, int n, int batch, void* L, doubl
 
 int sla_copy(sla_handle_t h, int dtype, int n, int batch, void* Lo, double* dout, void* Ro, const void* Li,
              const double* din, const void* Ri) {
+    if (is_f32(dtype)) return f32_copy(h, dtype, n, batch, Lo, dout, Ro, Li, din, Ri);
     CHECK_COMMON(h, dtype, n, batch);
     if (!Lo) return -5; if (!dout) return -6; if (!Ro) return -7; if (!Li) return -8; if (!din) return -9; if (!Ri) return -10;
     size_t es = dtype == SLA_F64 ? sizeof(double) : sizeof(cplx);
@@ -960,6 +988,7 @@ int sla_copy(sla_handle_t h, int dtype, int n, int batch, void* Lo, double* dout
 
 int sla_ldr_to_mat(sla_handle_t h, int dtype, int n, int batch, void* A, const void* L, const double* d,
                    const void* R, void* ws) {
+    if (is_f32(dtype)) return f32_ldr_to_mat(h, dtype, n, batch, A, L, d, R, ws, 0);
     CHECK_COMMON(h, dtype, n, batch);
     if (!A) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldr_to_mat_impl<double>(h, n, batch, (double*)A, (const double*)L, d, (const double*)R, ws);
@@ -968,6 +997,7 @@ int sla_ldr_to_mat(sla_handle_t h, int dtype, int n, int batch, void* A, const v
 
 int sla_adjoint(sla_handle_t h, int dtype, int n, int batch, void* At, const void* L, const double* d, const void* R,
                 void* ws) {
+    if (is_f32(dtype)) return f32_ldr_to_mat(h, dtype, n, batch, At, L, d, R, ws, 1);
     CHECK_COMMON(h, dtype, n, batch);
     if (!At) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return adjoint_impl<double>(h, n, batch, (double*)At, (const double*)L, d, (const double*)R, ws);
@@ -976,6 +1006,7 @@ int sla_adjoint(sla_handle_t h, int dtype, int n, int batch, void* At, const voi
 
 int sla_lmul_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U, long long strideU, void* L,
                      double* d, void* R, void* ws) {
+    if (is_f32(dtype)) return f32_mat_ldr(h, dtype, n, batch, U, strideU, L, d, R, ws, 0);
     CHECK_COMMON(h, dtype, n, batch);
     if (!U) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return lmul_mat_ldr_impl<double>(h, n, batch, (const double*)U, strideU, (double*)L, d, (double*)R, ws);
@@ -984,6 +1015,7 @@ int sla_lmul_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U,
 
 int sla_rmul_ldr_mat(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R, const void* V,
                      long long strideV, void* ws) {
+    if (is_f32(dtype)) return f32_ldr_mat(h, dtype, n, batch, L, d, R, V, strideV, ws, 0);
     CHECK_COMMON(h, dtype, n, batch);
     if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return rmul_ldr_mat_impl<double>(h, n, batch, (double*)L, d, (double*)R, (const double*)V, strideV, ws);
@@ -996,6 +1028,7 @@ int sla_rmul_ldr_mat(sla_handle_t h, int dtype, int n, int batch, void* L, doubl
 
 int sla_lmul_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, const void* UL, const double* Ud, const void* UR,
                      void* VL, double* Vd, void* VR, void* ws) {
+    if (is_f32(dtype)) return f32_ldr_ldr(h, dtype, n, batch, (void*)UL, (double*)Ud, (void*)UR, VL, Vd, VR, ws, 0);
     CHECK_COMMON(h, dtype, n, batch);
     UV_NULLCHECK();
     if (!ws) return -11; CLEAR_INFO(h, dtype, n, batch, ws);
@@ -1007,6 +1040,7 @@ int sla_lmul_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, const void* UL
 
 int sla_rmul_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, double* Ud, void* UR, const void* VL,
                      const double* Vd, const void* VR, void* ws) {
+    if (is_f32(dtype)) return f32_ldr_ldr(h, dtype, n, batch, UL, Ud, UR, (void*)VL, (double*)Vd, (void*)VR, ws, 2);
     CHECK_COMMON(h, dtype, n, batch);
     UV_NULLCHECK();
     if (!ws) return -11; CLEAR_INFO(h, dtype, n, batch, ws);
@@ -1018,6 +1052,7 @@ int sla_rmul_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, doub
 
 int sla_lmul_ldr_mat(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
                      void* V, void* ws) {
+    if (is_f32(dtype)) return f32_dense(h, dtype, n, batch, V, L, d, R, ws, 0);
     CHECK_COMMON(h, dtype, n, batch);
     if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return lmul_ldr_mat_impl<double>(h, n, batch, (const double*)L, d, (const double*)R, (double*)V, ws);
@@ -1026,6 +1061,7 @@ int sla_lmul_ldr_mat(sla_handle_t h, int dtype, int n, int batch, const void* L,
 
 int sla_rmul_mat_ldr(sla_handle_t h, int dtype, int n, int batch, void* U, const void* L, const double* d,
                      const void* R, void* ws) {
+    if (is_f32(dtype)) return f32_dense(h, dtype, n, batch, U, L, d, R, ws, 2);
     CHECK_COMMON(h, dtype, n, batch);
     if (!U) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return rmul_mat_ldr_impl<double>(h, n, batch, (double*)U, (const double*)L, d, (const double*)R, ws);
@@ -1033,6 +1069,7 @@ int sla_rmul_mat_ldr(sla_handle_t h, int dtype, int n, int batch, void* U, const
 }
 
 int sla_det_lu(sla_handle_t h, int dtype, int n, int batch, void* A, double* logdet, void* sign, void* ws) {
+    if (is_f32(dtype)) return f32_lu(h, dtype, n, batch, A, nullptr, logdet, sign, ws, 0);
     CHECK_COMMON(h, dtype, n, batch);
     if (!A) return -5; if (!ws) return -8; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return det_lu_impl<double>(h, n, batch, (double*)A, logdet, (double*)sign, ws);
@@ -1040,6 +1077,7 @@ int sla_det_lu(sla_handle_t h, int dtype, int n, int batch, void* A, double* log
 }
 
 int sla_inv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, double* logdet, void* sign, void* ws) {
+    if (is_f32(dtype)) return f32_lu(h, dtype, n, batch, A, nullptr, logdet, sign, ws, 1);
     CHECK_COMMON(h, dtype, n, batch);
     if (!A) return -5; if (!ws) return -8; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return inv_lu_impl<double>(h, n, batch, (double*)A, logdet, (double*)sign, ws);
@@ -1048,6 +1086,7 @@ int sla_inv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, double* log
 
 int sla_logabsdet(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
                   double* logdet, void* sign, void* ws) {
+    if (is_f32(dtype)) return f32_logabsdet(h, dtype, n, batch, L, d, R, logdet, sign, ws);
     CHECK_COMMON(h, dtype, n, batch);
     if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return logabsdet_impl<double>(h, n, batch, (const double*)L, d, (const double*)R, logdet, (double*)sign, ws);
@@ -1056,6 +1095,7 @@ int sla_logabsdet(sla_handle_t h, int dtype, int n, int batch, const void* L, co
 
 int sla_inv_IpA(sla_handle_t h, int dtype, int n, int batch, void* G, const void* L, const double* d, const void* R,
                 double* logdet, void* sign, void* ws) {
+    if (is_f32(dtype)) return f32_inv_IpA(h, dtype, n, batch, G, L, d, R, logdet, sign, ws);
     CHECK_COMMON(h, dtype, n, batch);
     if (!G) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -11; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return inv_IpA_impl<double>(h, n, batch, (double*)G, (const double*)L, d, (const double*)R, logdet, (double*)sign, ws);
@@ -1063,6 +1103,7 @@ int sla_inv_IpA(sla_handle_t h, int dtype, int n, int batch, void* G, const void
 }
 
 int sla_ldiv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, void* B, double* logdet, void* sign, void* ws) {
+    if (is_f32(dtype)) return f32_lu(h, dtype, n, batch, A, B, logdet, sign, ws, 2);
     CHECK_COMMON(h, dtype, n, batch);
     if (!A) return -5; if (!B) return -6; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldiv_lu_impl<double>(h, n, batch, (double*)A, (double*)B, logdet, (double*)sign, ws);
@@ -1071,6 +1112,7 @@ int sla_ldiv_lu(sla_handle_t h, int dtype, int n, int batch, void* A, void* B, d
 
 int sla_ldiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, const void* L, const double* d, const void* R,
                      void* V, void* ws) {
+    if (is_f32(dtype)) return f32_dense(h, dtype, n, batch, V, L, d, R, ws, 1);
     CHECK_COMMON(h, dtype, n, batch);
     if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldiv_ldr_mat_impl<double>(h, n, batch, (const double*)L, d, (const double*)R, (double*)V, ws);
@@ -1079,6 +1121,7 @@ int sla_ldiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, const void* L,
 
 int sla_ldiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, const void* UL, const double* Ud, const void* UR,
                      void* VL, double* Vd, void* VR, void* ws) {
+    if (is_f32(dtype)) return f32_ldr_ldr(h, dtype, n, batch, (void*)UL, (double*)Ud, (void*)UR, VL, Vd, VR, ws, 1);
     CHECK_COMMON(h, dtype, n, batch);
     UV_NULLCHECK();
     if (!ws) return -11; CLEAR_INFO(h, dtype, n, batch, ws);
@@ -1090,6 +1133,7 @@ int sla_ldiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, const void* UL
 
 int sla_ldiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U, long long strideU, void* L, double* d,
                      void* R, void* ws) {
+    if (is_f32(dtype)) return f32_mat_ldr(h, dtype, n, batch, U, strideU, L, d, R, ws, 1);
     CHECK_COMMON(h, dtype, n, batch);
     if (!U) return -5; if (!L) return -7; if (!d) return -8; if (!R) return -9; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return ldiv_mat_ldr_impl<double>(h, n, batch, (const double*)U, strideU, (double*)L, d, (double*)R, ws);
@@ -1098,6 +1142,7 @@ int sla_ldiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, const void* U,
 
 int sla_rdiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, void* U, const void* L, const double* d,
                      const void* R, void* ws) {
+    if (is_f32(dtype)) return f32_dense(h, dtype, n, batch, U, L, d, R, ws, 3);
     CHECK_COMMON(h, dtype, n, batch);
     if (!U) return -5; if (!L) return -6; if (!d) return -7; if (!R) return -8; if (!ws) return -9; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return rdiv_mat_ldr_impl<double>(h, n, batch, (double*)U, (const double*)L, d, (const double*)R, ws);
@@ -1106,6 +1151,7 @@ int sla_rdiv_mat_ldr(sla_handle_t h, int dtype, int n, int batch, void* U, const
 
 int sla_rdiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, double* Ud, void* UR, const void* VL,
                      const double* Vd, const void* VR, void* ws) {
+    if (is_f32(dtype)) return f32_ldr_ldr(h, dtype, n, batch, UL, Ud, UR, (void*)VL, (double*)Vd, (void*)VR, ws, 3);
     CHECK_COMMON(h, dtype, n, batch);
     UV_NULLCHECK();
     if (!ws) return -11; CLEAR_INFO(h, dtype, n, batch, ws);
@@ -1117,15 +1163,17 @@ int sla_rdiv_ldr_ldr(sla_handle_t h, int dtype, int n, int batch, void* UL, doub
 
 int sla_rdiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, void* L, double* d, void* R, const void* V,
                      long long strideV, void* ws) {
+    if (is_f32(dtype)) return f32_ldr_mat(h, dtype, n, batch, L, d, R, V, strideV, ws, 1);
     CHECK_COMMON(h, dtype, n, batch);
     if (!L) return -5; if (!d) return -6; if (!R) return -7; if (!V) return -8; if (!ws) return -10; CLEAR_INFO(h, dtype, n, batch, ws);
     if (dtype == SLA_F64) return rdiv_ldr_mat_impl<double>(h, n, batch, (double*)L, d, (double*)R, (const double*)V, strideV, ws);
     return rdiv_ldr_mat_impl<cplx>(h, n, batch, (cplx*)L, d, (cplx*)R, (const cplx*)V, strideV, ws);
 }
 
-#define DEFINE_UV(name, impl)                                                                                      \
+#define DEFINE_UV(name, impl, which)                                                                               \
     int name(sla_handle_t h, int dtype, int n, int batch, void* G, const void* UL, const double* Ud, const void* UR, \
              const void* VL, const double* Vd, const void* VR, double* logdet, void* sign, void* ws) {             \
+        if (is_f32(dtype)) return f32_inv_uv(h, dtype, n, batch, G, UL, Ud, UR, VL, Vd, VR, logdet, sign, ws, which); \
         CHECK_COMMON(h, dtype, n, batch);                                                                          \
         if (!G) return -5;                                                                                         \
         if (!UL) return -6; if (!Ud) return -7; if (!UR) return -8; if (!VL) return -9; if (!Vd) return -10;       \
@@ -1136,9 +1184,9 @@ int sla_rdiv_ldr_mat(sla_handle_t h, int dtype, int n, int batch, void* L, doubl
         return impl<cplx>(h, n, batch, (cplx*)G, (const cplx*)UL, Ud, (const cplx*)UR, (const cplx*)VL, Vd,         \
                           (const cplx*)VR, logdet, (cplx*)sign, ws);                                               \
     }
-DEFINE_UV(sla_inv_IpUV, inv_IpUV_impl)
-DEFINE_UV(sla_inv_UpV, inv_UpV_impl)
-DEFINE_UV(sla_inv_invUpV, inv_invUpV_impl)
+DEFINE_UV(sla_inv_IpUV, inv_IpUV_impl, 0)
+DEFINE_UV(sla_inv_UpV, inv_UpV_impl, 1)
+DEFINE_UV(sla_inv_invUpV, inv_invUpV_impl, 2)
 
 int sla_gemm(sla_handle_t h, int dtype, int opa, int opb, int m, int n, int k, const void* A, int lda,
              long long strideA, const void* B, int ldb, long long strideB, void* C, int ldc, long long strideC,
@@ -1182,12 +1230,14 @@ int sla_walker_sums(sla_handle_t h, int dtype, int batch, const double* logdet, 
 }
 
 size_t sla_greens_chain_workspace_bytes(int dtype, int n, int batch, int L, int n_stab) {
+    if (is_f32(dtype)) return f32_chain_workspace_bytes(dtype, n, batch, L, n_stab);
     if (n <= 0 || batch <= 0 || L <= 0 || n_stab <= 0 || L % n_stab) return 0;
     if ((dtype != SLA_F64 && dtype != SLA_C64) || !n_supported(dtype, n)) return 0;
     return dtype == SLA_F64 ? ChainWs<double>::bytes(n, batch, L, n_stab) : ChainWs<cplx>::bytes(n, batch, L, n_stab);
 }
 
 int* sla_greens_chain_workspace_info(void* ws, int dtype, int n, int batch, int L, int n_stab) {
+    if (is_f32(dtype)) dtype -= 2;
     if (!ws || n <= 0 || batch <= 0 || L <= 0 || n_stab <= 0 || L % n_stab) return nullptr;
     if (dtype == SLA_F64) return Ws<double>(ChainWs<double>(ws, n, batch, L, n_stab).ws, n, batch).info;
     return Ws<cplx>(ChainWs<cplx>(ws, n, batch, L, n_stab).ws, n, batch).info;
@@ -1196,6 +1246,7 @@ int* sla_greens_chain_workspace_info(void* ws, int dtype, int n, int batch, int 
 int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L, int n_stab, const void* expK,
                      const signed char* fields, double lam, int inverse, void* G, double* logdet, void* sign,
                      void* Lout, double* dout, void* Rout, void* ws, size_t ws_bytes) {
+    if (is_f32(dtype)) return f32_greens_chain(h, dtype, n, batch, L, n_stab, expK, fields, lam, inverse, G, logdet, sign, Lout, dout, Rout, ws, ws_bytes);
     CHECK_COMMON(h, dtype, n, batch);
     if (L <= 0) return -5;
     if (n_stab <= 0 || L % n_stab) return -6;
@@ -1211,12 +1262,14 @@ int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L, int n_s
 }
 
 size_t sla_sweep_workspace_bytes(int dtype, int n, int batch, int L, int n_stab) {
+    if (is_f32(dtype)) return f32_sweep_workspace_bytes(dtype, n, batch, L, n_stab);
     if (n <= 0 || batch <= 0 || L <= 0 || n_stab <= 0 || L % n_stab) return 0;
     if ((dtype != SLA_F64 && dtype != SLA_C64) || !n_supported(dtype, n)) return 0;
     return dtype == SLA_F64 ? SweepWs<double>::bytes(n, batch, L, n_stab) : SweepWs<cplx>::bytes(n, batch, L, n_stab);
 }
 
 int* sla_sweep_workspace_info(void* ws, int dtype, int n, int batch, int L, int n_stab) {
+    if (is_f32(dtype)) dtype -= 2;
     if (!ws || n <= 0 || batch <= 0 || L <= 0 || n_stab <= 0 || L % n_stab) return nullptr;
     if (dtype == SLA_F64) return Ws<double>(SweepWs<double>(ws, n, batch, L, n_stab).ws, n, batch).info;
     return Ws<cplx>(SweepWs<cplx>(ws, n, batch, L, n_stab).ws, n, batch).info;
@@ -1225,6 +1278,7 @@ int* sla_sweep_workspace_info(void* ws, int dtype, int n, int batch, int L, int 
 int sla_sweep(sla_handle_t h, int dtype, int n, int batch, int L, int n_stab, const void* expK, const void* expKinv,
               const signed char* fields, double lam, void* G0, void* G, double* logdet, void* sign, double* dG, void* ws,
               size_t ws_bytes) {
+    if (is_f32(dtype)) return f32_sweep(h, dtype, n, batch, L, n_stab, expK, expKinv, fields, lam, G0, G, logdet, sign, dG, ws, ws_bytes);
     CHECK_COMMON(h, dtype, n, batch);
     if (L <= 0) return -5;
     if (n_stab <= 0 || L % n_stab) return -6;

@@ -13,6 +13,7 @@ template <typename T> struct LdrArgs {
     double* d; long long stride_d;           // out: |diag R'|
     T* R; long long strideR; int ldr;        // out: D^-1 R' P^T
     T* Twork; long long strideT;             // scratch: ldr_twork_elems(n) elements per matrix
+    T* Qwork; long long strideQ;             // scratch n*n per matrix, multi-CTA kernel only (sla_ldr_mc.cu); may be null
     long long* jpvt_out;                     // optional: 1-based pivots (n per matrix), may be null
     long long* prof;                         // optional (diagnostics): per-phase cycle counters of cluster 0, may be null
     int* info;                               // optional per-matrix info: raised from 0 to LDR_INFO_RANGE (never cleared here)
@@ -44,6 +45,9 @@ void ldr_n256_resident(int* reg_clusters, int* hyb_clusters);
 // Factorises and forms Q (sla_orgq.cu); needs p.Twork with strideT >= n.
 template <typename T> cudaError_t ldr_blk_batched(const LdrArgs<T>& p, cudaStream_t s);
 template <typename T> int ldr_blk_cluster_size(int n);
+// multi-CTA L2-streaming kernel for large n and small batches (sla_ldr_mc.cu): a cluster of cs CTAs per matrix, needs p.Qwork
+template <typename T> cudaError_t ldr_mc_batched(const LdrArgs<T>& p, int cs, cudaStream_t s);
+template <typename T> bool ldr_mc_supported(int n);
 // Q = H_0...H_{n-1} I on the FP64 tensor cores after a factorisation-only launch (real, n <= 256; taus in p.Twork)
 cudaError_t orgq_dmma_batched(const LdrArgs<double>& p, cudaStream_t s);
 
@@ -86,6 +90,10 @@ template <typename T> cudaError_t combine_batched(const CombineArgs<T>& a, cudaS
 template <typename T> cudaError_t walker_sums_batched(double* out4, const double* logdet, const T* sign, int batch, cudaStream_t s);
 // out[b] = max |A[b] - B[b]| over the nn elements of matrix b (NaN if any difference is NaN)
 template <typename T> cudaError_t maxabsdiff_batched(double* out, const T* A, const T* B, long long nn, long long stride, int batch, cudaStream_t s);
+// Float32 storage types: element-wise promotion / demotion (count in REALS) and identity matrices in the storage type
+cudaError_t convert_f32_f64(double* dst, const float* src, long long count, cudaStream_t s);
+cudaError_t convert_f64_f32(float* dst, const double* src, long long count, cudaStream_t s);
+cudaError_t set_identity_f32(float* A, long long nn, int n, int batch, bool complex_, cudaStream_t s);
 // out[i] = multiplier realising ScaleMode `mode` with d[i] (feeds the GEMM epilogue, which only multiplies)
 cudaError_t scale_prep_batched(double* out, const double* d, int mode, long long count, cudaStream_t s);
 // ev[c,l,i] = exp(lam * s[c,l,i])

@@ -275,6 +275,44 @@ template <typename T> cudaError_t maxabsdiff_batched(double* out, const T* A, co
 template cudaError_t maxabsdiff_batched<double>(double*, const double*, const double*, long long, long long, int, cudaStream_t);
 template cudaError_t maxabsdiff_batched<cplx>(double*, const cplx*, const cplx*, long long, long long, int, cudaStream_t);
 
+// ---- Float32 storage types (sla_capi_f32.cu): promotion / demotion of operand arrays, identity in the storage type
+__global__ void cvt_f32_f64_kernel(double* dst, const float* src, long long count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = (double)src[i];
+}
+__global__ void cvt_f64_f32_kernel(float* dst, const double* src, long long count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) dst[i] = (float)src[i];   // round to nearest even; out-of-range values become +-Inf like a Float32 store
+}
+__global__ void identity_f32_kernel(float* A, long long nn, int n, int reals, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long e = i / reals;            // element index over the batch
+    const int part = (int)(i % reals);
+    const long long m = e % nn;
+    A[i] = (part == 0 && (m / n) == (m % n)) ? 1.0f : 0.0f;
+}
+cudaError_t convert_f32_f64(double* dst, const float* src, long long count, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    cvt_f32_f64_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(dst, src, count);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+cudaError_t convert_f64_f32(float* dst, const double* src, long long count, cudaStream_t s) {
+    if (count <= 0) return cudaSuccess;
+    cvt_f64_f32_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(dst, src, count);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+cudaError_t set_identity_f32(float* A, long long nn, int n, int batch, bool complex_, cudaStream_t s) {
+    const int reals = complex_ ? 2 : 1;
+    const long long total = nn * batch * reals;
+    if (total <= 0) return cudaSuccess;
+    identity_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(A, nn, n, reals, total);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+
 template <typename T> cudaError_t walker_sums_batched(double* out4, const double* logdet, const T* sign, int batch, cudaStream_t s) {
     walker_sums_kernel<T><<<1, 256, 0, s>>>(out4, logdet, sign, batch);
     ++g_launch_count;

@@ -539,7 +539,7 @@ def check_chain_full_batch(S, cfg, sample, inverse, expect_algo):
 
 
 # which factorisation kernel the dispatcher must pick at the full batch of each BASELINE config
-BENCH_ALGO = {"C2": "hybrid", "C3": "streaming", "C4": "streaming", "C5": "streaming"}
+BENCH_ALGO = {"C2": "hybrid", "C3": "streaming", "C4": "multicta", "C5": "streaming"}
 
 
 def test_chain_C2_full_batch(S):
@@ -698,7 +698,7 @@ def test_ldr_hybrid_shape_edge_inputs(S):
             assert relerr((L[b] * d[b][None, :]) @ R[b], B[b]) < 1e-12
 
 
-@pytest.mark.parametrize("algo", ["streaming", "cluster", "hyb", "hyb+oneq", "hyb+qvec", "blk"])
+@pytest.mark.parametrize("algo", ["streaming", "cluster", "hyb", "hyb+oneq", "hyb+qvec", "blk", "mc", "mc+cs2", "mc+cs8"])
 def test_other_ldr_kernels_subprocess(algo):
     """Default LDR kernel for n <= 256 is the register-resident cluster kernel.  The shared-memory cluster
     kernel (256 < n <= 512, e.g. C5's N=400) and the L2-streaming kernel (larger n, e.g. C4's N=1024) are
@@ -711,6 +711,8 @@ def test_other_ldr_kernels_subprocess(algo):
     env = dict(os.environ, SLA_LDR_ALGO=algo.split("+")[0])
     if algo.endswith("+oneq"):    # the hybrid shape with Q formed in the same launch (MODE 0) instead of a second one
         env["SLA_HYB_SPLITQ"] = "0"
+    if "+cs" in algo:             # the multi-CTA streaming kernel with clusters of 2 / 8 instead of 4
+        env["SLA_LDR_MC_CS"] = algo[-1]
     if algo.endswith("+qvec"):    # Q formed by the vector-unit MODE 2 launch instead of the tensor-core kernel (sla_orgq.cu)
         env["SLA_Q_DMMA"] = "0"
     # only tests whose sizes the forced kernel exists for (a forced kernel that does not apply is an error)
@@ -719,7 +721,10 @@ def test_other_ldr_kernels_subprocess(algo):
     else:
         sel = ("ldr_random or ldr_graded or ldr_identity or ldr_hybrid or chain_C1 or ref_lmul_matrix or small_complex "
                "or forced_algo_ran")
-    env["SLA_EXPECT_ALGO"] = {"streaming": "streaming", "cluster": "cluster", "blk": "blocked"}.get(algo, "hybrid")
+    if algo.startswith("mc"):       # any n; the sizes it is dispatched for by default (n > 512) included
+        sel += " or ldr_n512_and_n1024"
+    env["SLA_EXPECT_ALGO"] = {"streaming": "streaming", "cluster": "cluster", "blk": "blocked", "mc": "multicta",
+                              "mc+cs2": "multicta", "mc+cs8": "multicta"}.get(algo, "hybrid")
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", sel],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
@@ -741,6 +746,10 @@ def test_ldr_n512_and_n1024_paths(S):
     rng = np.random.default_rng(9)
     check_ldr(S, graded_matrix(rng, 400, False, 50, 1))
     check_ldr(S, rand_matrix(rng, 520, False, 1))
+    # n > 512 with a small batch: the multi-CTA streaming kernel (clusters of 8 at batch <= 14, of 4 up to 33)
+    check_ldr(S, graded_matrix(rng, 1024, False, 60, 2))
+    check_ldr(S, rand_matrix(rng, 600, True, 3))
+    check_ldr(S, rand_matrix(rng, 530, False, 20))
 
 
 # ------------------------------------------------------------------- fused sweep stepper vs the oracle
@@ -802,8 +811,90 @@ def test_sweep_C2_properties(S):
     worst = check_sweep(S, cfg, list(range(cfg.chains)), n_oracle=1)
     expK, expKinv, fields, out = run_sweep(S, cfg, list(range(cfg.chains)))
     scale = np.abs(out["G0"]).max(axis=(1, 2))
-    assert np.all(np.abs(out["G"] - out["G0"]).max(axis=(1, 2)) / scale < 1e-9)
+    # two different stabilisation routes to the same matrix, each within ~1e-10 of it (chain 0 above: 1e-10 vs the oracle)
+    assert np.all(np.abs(out["G"] - out["G0"]).max(axis=(1, 2)) / scale < 1e-8)
     assert np.all(np.abs(out["logdet"] - out["logdet"][0:1]) < 1e-8 * np.abs(out["logdet"][0:1]))
     assert np.all(out["sign"] == out["sign"][0:1])
     assert np.all(out["dG"] < 1e-6)
     print(f"[parity] sweep C2 (64 chains): max rel err vs oracle {worst:.2e}, max wrap error {out['dG'].max():.2e}")
+
+
+# ------------------------------------------------------------------- Float32 / ComplexF32 storage types
+# The reference generates its LAPACK wrappers for all four element types (src/qr.jl:29-32, src/lu.jl:26-29); here the
+# single-precision types are storage types computed in FP64, so the comparison is against the FP64 oracle on the same
+# (Float32-rounded) inputs with Float32 tolerances: 5e-6 for one operation, 1e-4 for chains of demoted operations.
+F32_ONE, F32_CHAIN = 5e-6, 1e-4
+
+
+@pytest.mark.parametrize("complex_", [False, True])
+@pytest.mark.parametrize("n", [16, 64, 200])
+def test_f32_ldr_and_inverse(S, n, complex_):
+    rng = np.random.default_rng(500 + n)
+    A = rand_matrix(rng, n, complex_, 3).astype(np.complex64 if complex_ else np.float32)
+    dA = S.to_device(A)
+    assert dA.dtype == (torch.complex64 if complex_ else torch.float32)
+    ws = S.ldr_workspace(dA)
+    F = S.ldr(dA, ws)
+    assert F.L.dtype == dA.dtype and F.R.dtype == dA.dtype and F.d.dtype == torch.float64
+    L, d, R = S.to_host(F.L).astype(np.complex128), F.d.cpu().numpy(), S.to_host(F.R).astype(np.complex128)
+    A64 = A.astype(np.complex128)
+    for b in range(3):
+        assert relerr((L[b] * d[b][None, :]) @ R[b], A64[b]) < F32_ONE * 4
+        assert np.max(np.abs(L[b].conj().T @ L[b] - np.eye(n))) < F32_ONE * 4
+    G = torch.empty_like(dA)
+    logdet, sign = S.inv_IpA_(G, F, ws)
+    Gh = S.to_host(G).astype(np.complex128)
+    for b in range(3):
+        ref = np.linalg.inv(np.eye(n) + A64[b])
+        assert relerr(Gh[b], ref) < F32_CHAIN
+        sr, lr = np.linalg.slogdet(ref)
+        assert abs(logdet[b].item() - lr) < F32_CHAIN * max(1.0, abs(lr))
+        assert abs(complex(sign[b].item()) - sr) < F32_CHAIN
+    # round trip through copyto!(A, F) and the dense product lmul!(F, V)
+    B = torch.empty_like(dA)
+    S.copyto_(B, F, ws)
+    assert relerr(S.to_host(B).astype(np.complex128), A64) < F32_ONE * 4
+
+
+def test_f32_chain_and_sweep(S):
+    cfg = S.synthetic.HubbardConfig("f", 6, 60, 10, 3)
+    expK32 = cfg.expK().astype(np.float32)
+    fields = cfg.fields([0, 1, 2])
+    G, logdet, sign, _ = S.greens_chain(S.to_device(expK32), torch.from_numpy(fields).cuda(), cfg.lam, cfg.n_stab, "IpA")
+    assert G.dtype == torch.float32 and sign.dtype == torch.float32 and logdet.dtype == torch.float64
+    expK = expK32.astype(np.float64)
+    for i in range(3):
+        Gr, lr, sr, _ = ochain.eval_greens(expK, fields[i], cfg.lam, cfg.n_stab, "IpA")
+        assert relerr(S.to_host(G)[i].astype(np.float64), Gr) < F32_ONE
+        assert abs(logdet[i].item() - lr) <= 1e-10 * max(1.0, abs(lr))      # log|det| is carried in Float64
+        assert sign[i].item() == sr
+    from oracle import sweep as osweep
+    expKinv32 = np.linalg.inv(expK).astype(np.float32)
+    out = S.sweep(S.to_device(expK32), S.to_device(expKinv32), torch.from_numpy(fields).cuda(), cfg.lam, cfg.n_stab)
+    ref = osweep.sweep(expK, expKinv32.astype(np.float64), fields[0], cfg.lam, cfg.n_stab)
+    assert relerr(S.to_host(out["G"])[0].astype(np.float64), ref["G"]) < F32_ONE
+    assert relerr(S.to_host(out["G0"])[0].astype(np.float64), ref["G0"]) < F32_ONE
+    assert np.all(np.abs(out["logdet"][1:, 0].cpu().numpy() - ref["logdet"]) < 1e-6 * np.abs(ref["logdet"]))
+
+
+def test_c32_chain_IpUV_and_ops(S):
+    cfg = S.synthetic.HubbardConfig("fc", 4, 40, 10, 2, dtype=np.complex128, phase=0.3, inverse="IpUV")
+    expK = cfg.expK().astype(np.complex64)
+    fields = cfg.fields([0, 1])
+    G, logdet, sign, _ = S.greens_chain(S.to_device(expK), torch.from_numpy(fields).cuda(), cfg.lam, cfg.n_stab, "IpUV")
+    assert G.dtype == torch.complex64
+    for i in range(2):
+        Gr, lr, sr, _ = ochain.eval_greens(expK.astype(np.complex128), fields[i], cfg.lam, cfg.n_stab, "IpUV")
+        assert relerr(S.to_host(G)[i].astype(np.complex128), Gr) < F32_ONE
+        assert abs(complex(sign[i].item()) - sr) < F32_ONE
+    # op-level route: lmul!(B_bar, F) with demotion after every call, then inv_IpA!
+    Bbars = ochain.group_products(expK.astype(np.complex128), fields[0], cfg.lam, cfg.n_stab)
+    dB = [S.to_device(B.astype(np.complex64)) for B in Bbars]
+    ws = S.ldr_workspace(dB[0])
+    F = S.ldr(dB[0])
+    for B in dB:
+        S.lmul_(B, F, ws)
+    G2 = torch.empty_like(dB[0])
+    S.inv_IpA_(G2, F, ws)
+    Gr, _, _, _ = ochain.eval_greens(expK.astype(np.complex128), fields[0], cfg.lam, cfg.n_stab, "IpA")
+    assert relerr(S.to_host(G2)[0].astype(np.complex128), Gr) < F32_CHAIN
