@@ -31,6 +31,13 @@ template <typename T, int OPA, int OPB> static cudaError_t gemm_pick_tile(const 
 }
 
 template <typename T> cudaError_t gemm_batched(int opa, int opb, const GemmArgs<T>& p, cudaStream_t s) {
+    if constexpr (!is_cplx<T>::value) {
+        // one A for the whole batch (the group products expK * X): persistent A-stationary TMA kernel where the shape fits
+        if (opa == OP_N && opb == OP_N && p.strideA == 0) {
+            const cudaError_t e = gemm_shared_a_batched(p, s);
+            if (e != cudaErrorNotSupported) return e;
+        }
+    }
     if (opa == OP_N && opb == OP_N) return gemm_pick_tile<T, OP_N, OP_N>(p, s);
     if (opa == OP_C && opb == OP_N) return gemm_pick_tile<T, OP_C, OP_N>(p, s);
     if (opa == OP_N && opb == OP_C) return gemm_pick_tile<T, OP_N, OP_C>(p, s);

@@ -5,6 +5,8 @@
 namespace sla {
 
 template <typename T> cudaError_t gemm_batched(int opa, int opb, const GemmArgs<T>& p, cudaStream_t s);
+// persistent A-stationary TMA kernel for a shared A (strideA = 0), real, N/N (sla_gemm_sa.cu); cudaErrorNotSupported = not this shape
+cudaError_t gemm_shared_a_batched(const GemmArgs<double>& p, cudaStream_t s);
 
 // ---- LDR factorisation (sla_ldr.cu) -------------------------------------------------------
 template <typename T> struct LdrArgs {

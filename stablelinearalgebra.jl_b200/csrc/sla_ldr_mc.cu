@@ -56,7 +56,7 @@ template <typename T> __host__ __device__ inline size_t mc_smem_bytes(int n, int
     b += (size_t)NB * sizeof(T);               // auxv
     b += 2 * (size_t)n * sizeof(double);       // vn1, vn2
     b += 32 * sizeof(double);                  // redv
-    b += 2 * MC_MAXCS * sizeof(McMsg);         // msgs
+    b += 2 * MC_MAXCS * sizeof(McMsg) + 16;    // msgs (+ alignment)
     b += 2 * (size_t)n * sizeof(int);          // colidx, flag list
     b += 64 * sizeof(int);                     // redi + nflag
     return b + 64;
@@ -76,6 +76,7 @@ template <typename T> __device__ inline McSmem<T> mc_carve(unsigned char* raw, i
     s.vn1 = dd; dd += n;
     s.vn2 = dd; dd += n;
     s.redv = dd; dd += 32;
+    dd = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(dd) + 15) & ~(uintptr_t)15);   // odd n: McMsg is 16-byte aligned
     s.msgs = reinterpret_cast<McMsg*>(dd); dd += 2 * MC_MAXCS * (sizeof(McMsg) / sizeof(double));
     int* ii = reinterpret_cast<int*>(dd);
     s.colidx = ii; ii += n;

@@ -72,6 +72,33 @@ def test_gemm_ops(S, n, complex_):
     assert relerr(S.to_host(C), ref + A @ B) < 1e-13
 
 
+@pytest.mark.parametrize("n,batch", [(256, 16), (128, 9), (256, 150), (384, 8)])
+def test_gemm_shared_a(S, n, batch):
+    """One A for the whole batch (stride 0), plain and accumulate, at the shapes of the group products."""
+    rng = np.random.default_rng(n + batch)
+    A, B = rand_matrix(rng, n, False, 1), rand_matrix(rng, n, False, batch)
+    dA, dB = S.to_device(A), S.to_device(B)
+    C = torch.zeros_like(dB)
+    S.gemm(C, dA, dB)
+    ref = A @ B
+    assert relerr(S.to_host(C), ref) < 1e-13
+    S.gemm(C, dA, dB, accumulate=True)
+    assert relerr(S.to_host(C), 2 * ref) < 1e-13
+
+
+def test_gemm_shared_a_tma_kernel_subprocess():
+    """The persistent A-stationary TMA kernel (csrc/sla_gemm_sa.cu; opt-in through SLA_GEMM_SA=1: strideA = 0, real,
+    M % 64 = N % 128 = K % 16 = 0, K <= 256) must give the same answers; K = 384 must fall through to the generic one."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("SLA_GEMM_SA"):
+        pytest.skip("already in the child")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", "gemm_shared_a and not subprocess or chain_C2_sample"],
+                       env=dict(os.environ, SLA_GEMM_SA="1"), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 # -------------------------------------------------------------------------------------------- LDR
 def check_ldr(S, A, tol=2e-13):
     batch, n, _ = A.shape
