@@ -464,6 +464,126 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def sweep_flops(cfg):
+    """Algorithmic FLOPs of one stabilised sweep of one chain: group products 2N^3(L - L/n_stab),
+    stack of left factorisations (2 + 8/3 + 2)N^3 per group, inv_IpA! 6N^3, wrapping 4N^3 per slice, and per group
+    lmul! (2 + 8/3 + 2)N^3 + inv_IpUV! 38/3 N^3; x4 for complex."""
+    c = 4.0 if cfg.dtype.kind == "c" else 1.0
+    ng = cfg.L // cfg.n_stab
+    return c * cfg.N ** 3 * (2.0 * (cfg.L - ng) + ng * (20.0 / 3.0) + 6.0 + 4.0 * cfg.L + ng * (20.0 / 3.0 + 38.0 / 3.0))
+
+
+def run_sweep(args):
+    """`--workload sweep`: the fused sweep stepper (sla_sweep) on one BASELINE config -- a secondary
+    record, same JSON contract (value device-resident, e2e through host buffers, parity against oracle/sweep.py)."""
+    import torch
+    import torch.distributed as dist
+
+    import sla_b200 as sla
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg, chain_ids, total_chains = get_cfg(args.config, args.chains, args.scaling, world, rank)
+    n, L, chains, ng = cfg.N, cfg.L, cfg.chains, cfg.L // cfg.n_stab
+    dt = torch.complex128 if cfg.dtype.kind == "c" else torch.float64
+    expK = cfg.expK()
+    expKinv = np.linalg.inv(expK)
+    expK_h = torch.from_numpy(np.ascontiguousarray(expK.T)).pin_memory()
+    expKinv_h = torch.from_numpy(np.ascontiguousarray(expKinv.T)).pin_memory()
+    fields_h = torch.from_numpy(cfg.fields(chain_ids)).pin_memory()
+    expK_d, expKinv_d, fields_d = expK_h.cuda()[None], expKinv_h.cuda()[None], fields_h.cuda()
+    out = sla.sweep(expK_d, expKinv_d, fields_d, cfg.lam, cfg.n_stab)
+    bufs = {k: out[k] for k in ("G", "G0", "logdet", "sign", "dG")}
+    ws = out["ws"]
+    host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in bufs.items() if k != "G0"}
+    lib = sla.load()
+
+    def step_device():
+        sla.sweep(expK_d, expKinv_d, fields_d, cfg.lam, cfg.n_stab, ws=ws, **bufs)
+
+    def step_e2e():
+        ek = expK_h.to("cuda", non_blocking=True)[None]
+        eki = expKinv_h.to("cuda", non_blocking=True)[None]
+        fd = fields_h.to("cuda", non_blocking=True)
+        sla.sweep(ek, eki, fd, cfg.lam, cfg.n_stab, ws=ws, **bufs)
+        for k, h in host.items():
+            h.copy_(bufs[k], non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    steps = args.steps if args.steps is not None else max(2, DEFAULT_STEPS.get(cfg.name, 10) // 4)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step_device()
+    l0 = lib.sla_launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(step_device, steps)
+    clocks = sampler.stop() if sampler else None
+    launches = (lib.sla_launch_count() - l0) // steps
+    step_e2e()
+    ms_e2e = timed(step_e2e, steps)
+    parity = cpub = roof = None
+    if rank == 0:
+        peak = measure_dgemm_peak(torch)
+        tfl = sweep_flops(cfg) * chains / (ms_total / steps * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "whole sweep (GEMM-dominated: group products, wrapping, stabilisation)",
+                "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak, "traffic": None,
+                "peak_source": "FP64 cuBLAS DGEMM 8192^3 via torch.matmul measured in this run"}
+        if world == 1 and not args.no_cpu:
+            from oracle import sweep as osweep
+            t0 = time.perf_counter()
+            ref = osweep.sweep(expK, expKinv, cfg.fields(chain_ids[:1])[0], cfg.lam, cfg.n_stab)
+            dt_cpu = time.perf_counter() - t0
+            cpub = {"value": 1.0 / dt_cpu, "unit": "sweeps/s", "cores": int(os.environ.get("OMP_NUM_THREADS", host_cores()[0])),
+                    "kind": "port", "sample": f"1 chain of the same workload, {dt_cpu:.2f} s wall; numpy/LAPACK restatement "
+                    "oracle/sweep.py (one process, the BLAS library's own threads)"}
+            Gg = sla.to_host(bufs["G"][:1])[0]
+            ldg, sgg = bufs["logdet"][:, 0].cpu().numpy(), bufs["sign"][:, 0].cpu().numpy()
+            lref = np.concatenate([[ref["logdet0"]], ref["logdet"]])
+            sref = np.concatenate([[ref["sign0"]], ref["sign"]])
+            parity = {"chains_checked": 1, "max_rel_err_G": float(np.max(np.abs(Gg - ref["G"])) / np.max(np.abs(ref["G"]))),
+                      "max_abs_err_logdet": float(np.max(np.abs(ldg - lref))), "sign_mismatch": int(np.sum(np.abs(sgg - sref) > 1e-9)),
+                      "max_wrap_error_gpu": float(bufs["dG"].max().item()), "max_wrap_error_cpu": float(ref["dG"].max())}
+        h2d = 2 * expK_h.numel() * expK_h.element_size() + fields_h.numel()
+        d2h = sum(t.numel() * t.element_size() for t in host.values())
+        line = {"metric": "stabilised DQMC sweeps/sec (setup stack + L wraps + L/n_stab re-stabilisations per chain), "
+                          "fields fixed; max rel err vs CPU", "value": total_chains * steps / (ms_total * 1e-3),
+                "unit": "sweeps/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_total / steps,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "c128" if cfg.dtype.kind == "c" else "f64", "data": "synthetic",
+                "config": dict(config_json(cfg, world, {"l2_policy": f"working set per step ({ws.numel() / 2**30:.2f} GiB) is larger than the 126 MB L2"},
+                                           total_chains, args.scaling), workload=f"sweep stepper on {cfg.name}: {total_chains} chains, N={n}, L={L}, n_stab={cfg.n_stab}",
+                               flops_per_sweep=sweep_flops(cfg)),
+                "e2e": {"value": total_chains * steps / (ms_e2e * 1e-3), "unit": "sweeps/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpub, "parity": parity}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -477,9 +597,13 @@ def main():
                     help="chains per GPU (weak) or in total (strong); default: the config's")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--workload", default="greens", choices=["greens", "sweep"],
+                    help="greens: stabilised G(tau=0) evaluations (the BASELINE metric); sweep: the fused sweep stepper")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sweep":
+        run_sweep(args)
     else:
         run_gpu(args)
 
