@@ -565,7 +565,8 @@ def run_sweep(args):
             sref = np.concatenate([[ref["sign0"]], ref["sign"]])
             parity = {"chains_checked": 1, "max_rel_err_G": float(np.max(np.abs(Gg - ref["G"])) / np.max(np.abs(ref["G"]))),
                       "max_abs_err_logdet": float(np.max(np.abs(ldg - lref))), "sign_mismatch": int(np.sum(np.abs(sgg - sref) > 1e-9)),
-                      "max_wrap_error_gpu": float(bufs["dG"].max().item()), "max_wrap_error_cpu": float(ref["dG"].max())}
+                      "max_wrap_error_chain0_gpu": float(bufs["dG"][:, 0].max().item()), "max_wrap_error_chain0_cpu": float(ref["dG"].max()),
+                      "max_wrap_error_all_chains_gpu": float(bufs["dG"].max().item())}
         h2d = 2 * expK_h.numel() * expK_h.element_size() + fields_h.numel()
         d2h = sum(t.numel() * t.element_size() for t in host.values())
         line = {"metric": "stabilised DQMC sweeps/sec (setup stack + L wraps + L/n_stab re-stabilisations per chain), "

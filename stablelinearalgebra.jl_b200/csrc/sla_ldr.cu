@@ -17,8 +17,21 @@
 //     per-column GEMV produces anyway, and reused to form Q = H_1...H_n blockwise (backward
 //     accumulation, two DMMA products per panel).
 // Householder conventions are LAPACK's (?larfg): beta = -sign(Re alpha)*||(alpha,x)||, H = I - tau v v^H.
+#include <cstdio>
+
 #include "sla_cta.cuh"
 #include "sla_kernels.h"
+
+// -DSLA_LDRS_PROFILE: per-phase cycle counters of CTA 0 (thread 0), printed at the end of the kernel
+#ifdef SLA_LDRS_PROFILE
+#define SP_DECL long long sp_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long spt_ = clock64();
+#define SP(i) do { long long t_ = clock64(); sp_[i] += t_ - spt_; spt_ = t_; } while (0)
+#define SP_DUMP() do { if (blockIdx.x == 0 && threadIdx.x == 0) printf("ldr_kernel n=%d: init %lld | P1 fetch+apply %lld | P2 reflector %lld | scale+store %lld | GEMV %lld | gram %lld | P4 finish/downdate %lld | flagged %lld | argmax tail %lld | T + rank update %lld | R extract %lld | Q formation %lld\n", n, sp_[0], sp_[1], sp_[2], sp_[3], sp_[4], sp_[5], sp_[6], sp_[7], sp_[8], sp_[9], sp_[10], sp_[11]); } while (0)
+#else
+#define SP_DECL
+#define SP(i) do { } while (0)
+#define SP_DUMP() do { } while (0)
+#endif
 
 namespace sla {
 
@@ -168,6 +181,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
     T* Tw = p.Twork + (long long)b * p.strideT;
     const bool vec = (sizeof(T) == 8) && ((lda & 1) == 0) && ((n & 1) == 0) && ((((uintptr_t)A) & 15) == 0);
 
+    SP_DECL
     // ---------------------------------------------------------------- init: column norms, jpvt
     const T* Ain = p.Ain ? p.Ain + (long long)b * p.strideAin : nullptr;
     for (int c = warp; c < n; c += CTA_WARPS) {
@@ -198,6 +212,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
         if (pvt >= n) pvt = 0;  // all-NaN guard
     }
 
+    SP(0);
     // ---------------------------------------------------------------- pivoted QR, panel by panel
     for (int p0 = 0; p0 < n; p0 += NB) {
         const int jb = min(NB, n - p0);
@@ -205,6 +220,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
         for (int j = 0; j < jb; ++j) {
             const int k = p0 + j;
             T* vj = s.Vs + (size_t)j * ld;
+            SP(9);
             // ---- P1: bring the pivot column to position k, apply the panel's reflectors to it
             double ss = 0.0;
             for (int r = tid; r < n; r += CTA_THREADS) {
@@ -225,6 +241,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
             ss = warp_sum(ss);
             if (lane == 0) s.redv[warp] = ss;
             __syncthreads();
+            SP(1);
             // ---- P2: Householder reflector (LAPACK ?larfg)
             double xnorm2 = 0.0;
 #pragma unroll
@@ -240,6 +257,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
                 scal = mk<T>(1.0) / (alpha - mk<T>(beta));
             }
             __syncthreads();  // everyone has read vj[k] and redv
+            SP(2);
             for (int r = tid; r < n; r += CTA_THREADS) {
                 if (r > k) {
                     T v = vj[r] * scal;
@@ -259,8 +277,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
             }
             if (tid == CTA_THREADS - 2) s.tau[k] = tau;
             __syncthreads();
+            SP(3);
             // ---- P3: one pass over the trailing matrix: F(c,j) = tau * A(k:n,c)^H v ; Gram dots
             trailing_gemv<T, 4>(A, lda, k + 1, n, vj, k, tau, s.Fs + (size_t)j * ld, vec);
+            SP(4);
             for (int i = warp; i < j; i += CTA_WARPS) {
                 const T* vi = s.Vs + (size_t)i * ld;
                 T acc = mk<T>(0.0);
@@ -270,6 +290,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
             }
             if (tid == 0) *s.nflag = 0;
             __syncthreads();
+            SP(5);
             // ---- P4: finish F(:,j), update pivot row k, down-date the partial norms
             double bv = -1.0; int bi = 0x7fffffff;
             for (int c = k + 1 + tid; c < n; c += CTA_THREADS) {
@@ -299,6 +320,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
             warp_argmax(bv, bi);
             if (lane == 0) { s.redv[warp] = bv; s.redi[warp] = bi; }
             __syncthreads();
+            SP(6);
             const int nflag = *s.nflag;
             if (nflag > 0) {
                 // exact recomputation of the flagged columns' norms below row k (panel applied on the fly)
@@ -321,6 +343,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
                     if (v > bv) { bv = v; bi = c; }
                 }
                 pvt = block_argmax(bv, bi, s.redv, s.redi);
+                SP(7);
             } else {
                 double fv = s.redv[0]; int fidx = s.redi[0];
 #pragma unroll
@@ -332,6 +355,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
                 __syncthreads();
             }
             if (pvt >= n) pvt = min(k + 1, n - 1);
+            SP(8);
         }
         // ---- panel done: T factor (one warp) || rank-jb trailing update (everyone)
         const int kend = p0 + jb;
@@ -357,6 +381,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
         __syncthreads();
     }
 
+    SP(9);
     // ---------------------------------------------------------------- d = |diag R'|, R = D^-1 R' P^T
     {
         double* d = p.d + (long long)b * p.stride_d;
@@ -373,6 +398,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
             for (int c = tid; c < n; c += CTA_THREADS) p.jpvt_out[(long long)b * n + c] = s.jpvt[c] + 1;
     }
     __syncthreads();
+    SP(10);
 
     // ---------------------------------------------------------------- Q = H_1 ... H_n (backward, blocked)
     const int npan = (n + NB - 1) / NB;
@@ -423,6 +449,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_kernel(LdrArgs<T> p) {
         cta_rank_update<T, false>(A, lda, p0, n, p0, n, s.Vs, s.Fs, ld, jb, n - 1);
         __syncthreads();
     }
+    SP(11);
+    SP_DUMP();
 }
 
 template <typename T> static int pick_nb(int n) {
