@@ -156,16 +156,27 @@ __device__ void cta_panel_dot(T* __restrict__ Ws, const T* __restrict__ Ps, int 
         T acc[4][2];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[j][0] = mk<T>(0.0); acc[j][1] = mk<T>(0.0); }
-#pragma unroll 4
-        for (int kk = k_lo; kk < r_hi; kk += 4) {
-            const int r = kk + fk;
-            T cf = (cvalid && r >= r_lo && r < r_hi) ? col[r] : mk<T>(0.0);
-            const int rc = min(r, n_clamp);
+        // eight row steps per trip: all eight global loads of C are in flight before the first DMMA (one L2 round trip
+        // per 32 rows instead of one per 4: this loop is latency-bound, profiles/ldr_stream_phases_r2.txt)
+        for (int kk0 = k_lo; kk0 < r_hi; kk0 += 32) {
+            T cf[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < nif) {
-                    T pf = conj_(Ps[(j * 8 + fi) * ld + rc]);
-                    mma_acc(acc[j], cf, pf);
+            for (int u = 0; u < 8; ++u) {
+                const int r = kk0 + 4 * u + fk;
+                cf[u] = (cvalid && r >= r_lo && r < r_hi) ? col[r] : mk<T>(0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = kk0 + 4 * u + fk;
+                if (kk0 + 4 * u < r_hi) {
+                    const int rc = min(r, n_clamp);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < nif) {
+                            T pf = conj_(Ps[(j * 8 + fi) * ld + rc]);
+                            mma_acc(acc[j], cf[u], pf);
+                        }
+                    }
                 }
             }
         }
