@@ -4,6 +4,7 @@
 // it reproduces; scratch use follows the reference's M / M' / M'' roles where that matters for the
 // documented aliasing rules.
 #include <cstdlib>
+#include <cstring>
 #include <new>
 
 #include "../../include/sla_b200.h"
@@ -25,6 +26,19 @@ struct sla_handle_s {
     cudaEvent_t ev_start = nullptr;
     cudaEvent_t ev_chunk[64] = {};
     int n_events = 0;
+    // fused chain driver: the ~100-350 launches of one call captured once into a CUDA graph and replayed while the
+    // arguments stay the same (small problems are bound by launch latency, and a multi-GPU host issues 8 x 200 launches
+    // per step from one socket); SLA_GRAPH=0 switches it off
+    struct ChainGraph {
+        bool used = false;
+        unsigned long long key[20] = {};
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long kernels = 0;            // kernel launches inside the graph (sla_launch_count)
+        unsigned long long algo_launches[8] = {};  // LDR factorisations per algorithm inside the graph
+        int last_algo = 0;
+    } graphs[4];
+    int graph_next = 0;
+    bool graph_broken = false;                     // a capture failed once on this handle: direct launches from then on
 };
 
 namespace {
@@ -606,6 +620,18 @@ template <typename T> struct ChainWs {
     }
 };
 
+// the low-priority side stream and its events (created once per handle, outside any graph capture)
+static int ensure_side_stream(sla_handle_t h) {
+    if (h->side != nullptr) return 0;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
+    CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+    for (int i = 0; i < 64; ++i) CK(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+    h->n_events = 64;
+    return 0;
+}
+
 template <typename T>
 int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const T* expK, const signed char* fields,
                       double lam, int inverse, T* G, double* logdet, T* sign, T* Lout, double* dout, T* Rout,
@@ -634,14 +660,7 @@ int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const
     // cluster LDR kernels cannot use.
     static const bool overlap = [] { const char* e = getenv("SLA_OVERLAP"); return !(e && e[0] == '0'); }();
     static const int SUB = [] { const char* e = getenv("SLA_OVERLAP_SUB"); int v = e ? atoi(e) : 2; return v > 0 ? v : 2; }();   // groups per sub-chunk
-    if (overlap && h->side == nullptr) {
-        int lo = 0, hi = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
-        CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
-        for (int i = 0; i < 64; ++i) CK(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
-        h->n_events = 64;
-    }
+    if (overlap) CKI(ensure_side_stream(h));
     for (int g0 = 0; g0 < ng; g0 += gc) {
         const int gcur = (ng - g0 < gc) ? (ng - g0) : gc;
         const int nsub = (gcur + SUB - 1) / SUB;
@@ -905,6 +924,8 @@ int sla_create(sla_handle_t* handle, void* stream) {
 
 int sla_destroy(sla_handle_t handle) {
     if (handle) {
+        for (auto& e : handle->graphs)
+            if (e.exec) cudaGraphExecDestroy(e.exec);
         if (handle->side) cudaStreamDestroy(handle->side);
         if (handle->ev_start) cudaEventDestroy(handle->ev_start);
         for (int i = 0; i < handle->n_events; ++i) cudaEventDestroy(handle->ev_chunk[i]);
@@ -1254,11 +1275,70 @@ int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L, int n_s
     if (inverse != SLA_INV_IPA && inverse != SLA_INV_IPUV) return -10;
     if (inverse == SLA_INV_IPUV && (L / n_stab) < 2) return -10;
     if (!G) return -11; if (!logdet) return -12; if (!sign) return -13; if (!ws) return -17;
-    if (dtype == SLA_F64)
-        return greens_chain_impl<double>(h, n, batch, L, n_stab, (const double*)expK, fields, lam, inverse, (double*)G,
-                                         logdet, (double*)sign, (double*)Lout, dout, (double*)Rout, ws, ws_bytes);
-    return greens_chain_impl<cplx>(h, n, batch, L, n_stab, (const cplx*)expK, fields, lam, inverse, (cplx*)G, logdet,
-                                   (cplx*)sign, (cplx*)Lout, dout, (cplx*)Rout, ws, ws_bytes);
+    auto direct = [&]() -> int {
+        if (dtype == SLA_F64)
+            return greens_chain_impl<double>(h, n, batch, L, n_stab, (const double*)expK, fields, lam, inverse, (double*)G,
+                                             logdet, (double*)sign, (double*)Lout, dout, (double*)Rout, ws, ws_bytes);
+        return greens_chain_impl<cplx>(h, n, batch, L, n_stab, (const cplx*)expK, fields, lam, inverse, (cplx*)G, logdet,
+                                       (cplx*)sign, (cplx*)Lout, dout, (cplx*)Rout, ws, ws_bytes);
+    };
+    static const bool graphs_on = !(getenv("SLA_GRAPH") && atoi(getenv("SLA_GRAPH")) == 0);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (!graphs_on || h->graph_broken || h->stream == nullptr /* legacy stream: not capturable */ ||
+        cudaStreamIsCapturing(h->stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+        return direct();
+    // ---- replay a graph captured for exactly these arguments, or capture one now
+    unsigned long long key[20] = {};
+    {
+        int i = 0;
+        key[i++] = (unsigned long long)dtype; key[i++] = (unsigned long long)n; key[i++] = (unsigned long long)batch;
+        key[i++] = (unsigned long long)L; key[i++] = (unsigned long long)n_stab; key[i++] = (unsigned long long)(uintptr_t)expK;
+        key[i++] = (unsigned long long)(uintptr_t)fields; memcpy(&key[i++], &lam, sizeof(double)); key[i++] = (unsigned long long)inverse;
+        key[i++] = (unsigned long long)(uintptr_t)G; key[i++] = (unsigned long long)(uintptr_t)logdet; key[i++] = (unsigned long long)(uintptr_t)sign;
+        key[i++] = (unsigned long long)(uintptr_t)Lout; key[i++] = (unsigned long long)(uintptr_t)dout; key[i++] = (unsigned long long)(uintptr_t)Rout;
+        key[i++] = (unsigned long long)(uintptr_t)ws; key[i++] = (unsigned long long)ws_bytes; key[i++] = (unsigned long long)(uintptr_t)h->stream;
+    }
+    sla_handle_s::ChainGraph* g = nullptr;
+    for (auto& e : h->graphs)
+        if (e.used && memcmp(e.key, key, sizeof(key)) == 0) { g = &e; break; }
+    if (g == nullptr) {
+        if (ensure_side_stream(h) != 0) return direct();
+        sla_handle_s::ChainGraph& e = h->graphs[h->graph_next];
+        h->graph_next = (h->graph_next + 1) % 4;
+        if (e.exec) { cudaGraphExecDestroy(e.exec); e.exec = nullptr; }
+        e.used = false;
+        const unsigned long long k0 = g_launch_count.load();
+        unsigned long long a0[8];
+        for (int i = 0; i < 8; ++i) a0[i] = h->ldr_algo_launches[i];
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); h->graph_broken = true; return direct(); }
+        const int rc = direct();
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        // the launches were recorded, not executed: take them out of the counters again (a replay adds them back)
+        const unsigned long long kernels = g_launch_count.load() - k0;
+        g_launch_count -= kernels;
+        for (int i = 0; i < 8; ++i) { e.algo_launches[i] = h->ldr_algo_launches[i] - a0[i]; h->ldr_algo_launches[i] = a0[i]; }
+        if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (rc < 0 || rc == SLA_ENOTIMPL) return rc;     // an argument error: nothing was launched, report it
+            h->graph_broken = true;
+            return direct();
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); e.exec = nullptr; h->graph_broken = true; return direct(); }
+        memcpy(e.key, key, sizeof(key));
+        e.kernels = kernels;
+        e.last_algo = h->last_ldr_algo;
+        e.used = true;
+        g = &e;
+    }
+    CK(cudaGraphLaunch(g->exec, h->stream));
+    g_launch_count += g->kernels;
+    for (int i = 0; i < 8; ++i) h->ldr_algo_launches[i] += g->algo_launches[i];
+    h->last_ldr_algo = g->last_algo;
+    return 0;
 }
 
 size_t sla_sweep_workspace_bytes(int dtype, int n, int batch, int L, int n_stab) {

@@ -621,6 +621,38 @@ def test_chain_C1(S):
     check_chain(S, cfg, list(range(4)), "IpA")
 
 
+def test_chain_graph_replay(S):
+    """On an explicit stream the fused driver captures its launches into a CUDA graph and replays it while the arguments
+    stay the same (sla_capi.cu: sla_greens_chain).  Capture, replay, and replay on NEW field values in the same buffer
+    must equal the direct launches of the legacy default stream bit for bit; the launch and LDR counters advance per
+    replay."""
+    cfg = S.synthetic.CONFIGS["C1"]
+    expK = S.to_device(cfg.expK())
+    f0 = torch.from_numpy(cfg.fields([0, 1, 2])).cuda()
+    f1 = torch.from_numpy(cfg.fields([7, 8, 9])).cuda()
+    ref0 = S.greens_chain(expK, f0, cfg.lam, cfg.n_stab, "IpA")
+    ref1 = S.greens_chain(expK, f1, cfg.lam, cfg.n_stab, "IpA")
+    torch.cuda.synchronize()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        fields = f0.clone()
+        G, logdet, sign, ws = S.greens_chain(expK, fields, cfg.lam, cfg.n_stab, "IpA")                  # capture + launch
+        st.synchronize()
+        assert torch.equal(G, ref0[0]) and torch.equal(logdet, ref0[1]) and torch.equal(sign, ref0[2])
+        k0, a0 = S.load().sla_launch_count(), S.ldr_algo_launches()
+        S.greens_chain(expK, fields, cfg.lam, cfg.n_stab, "IpA", G=G, logdet=logdet, sign=sign, ws=ws)  # replay
+        st.synchronize()
+        k1, a1 = S.load().sla_launch_count(), S.ldr_algo_launches()
+        assert torch.equal(G, ref0[0])
+        assert k1 - k0 > 50 and sum(a1.values()) - sum(a0.values()) == cfg.L // cfg.n_stab
+        fields.copy_(f1)
+        S.greens_chain(expK, fields, cfg.lam, cfg.n_stab, "IpA", G=G, logdet=logdet, sign=sign, ws=ws)  # replay, new data
+        st.synchronize()
+        assert torch.equal(G, ref1[0]) and torch.equal(logdet, ref1[1]) and torch.equal(sign, ref1[2])
+        info = S.greens_chain_info(ws, G.dtype, cfg.N, 3, cfg.L, cfg.n_stab).cpu().numpy()
+        assert not info.any()
+
+
 def test_chain_small_complex_IpUV(S):
     syn = S.synthetic
     cfg = syn.HubbardConfig("c", 6, 60, 10, 4, dtype=np.complex128, phase=0.3, inverse="IpUV")
