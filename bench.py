@@ -69,7 +69,9 @@ def config_json(cfg, n_gpus, extra=None, total=None, scaling="weak"):
          "N": cfg.N, "L": cfg.L, "n_stab": cfg.n_stab, "chains_per_gpu": cfg.chains,
          "chains_total": total, "eltype": "ComplexF64" if cfg.dtype.kind == "c" else "Float64",
          "inverse": "inv_" + cfg.inverse + "!", "parallelism": f"chains sharded over {n_gpus} GPU(s)",
-         "flops_per_eval": cfg.flops_per_eval()}
+         "flops_per_eval": cfg.flops_per_eval(),
+         "ldr_pivoting": "panel-restricted (SLA_LDR_PIVOT=panel; not the ?geqp3 pivot sequence)"
+                         if os.environ.get("SLA_LDR_PIVOT", "").startswith("p") else "geqp3 (greedy, as the reference)"}
     if extra:
         c.update(extra)
     return c
@@ -621,9 +623,14 @@ def main():
                     help="chains per GPU (weak) or in total (strong); default: the config's")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--ldr-pivoting", default="geqp3", choices=["geqp3", "panel"],
+                    help="geqp3: the reference's greedy column pivoting (default, strict); panel: panel-restricted pivoting "
+                         "(SLA_LDR_PIVOT=panel, SURVEY 8(f)-4) -- a different pivot sequence, reported as its own record")
     ap.add_argument("--workload", default="greens", choices=["greens", "sweep"],
                     help="greens: stabilised G(tau=0) evaluations (the BASELINE metric); sweep: the fused sweep stepper")
     args = ap.parse_args()
+    if args.ldr_pivoting == "panel":
+        os.environ["SLA_LDR_PIVOT"] = "panel"      # read once by the library at its first factorisation
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "sweep":

@@ -154,8 +154,11 @@ template <typename T> struct Ctx {
             const char* e = getenv("SLA_LDR_ALGO");
             if (getenv("SLA_LDR_STREAMING")) return 3;
             if (!e) return 0;
-            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : (e[0] == 'h' ? 4 : (e[0] == 'b' ? 5 : (e[0] == 'm' ? 6 : 0)))));
+            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : (e[0] == 'h' ? 4 : (e[0] == 'b' ? 5 : (e[0] == 'm' ? 6 : (e[0] == 'p' ? 7 : 0))))));
         }();
+        // SLA_LDR_PIVOT=panel: panel-restricted pivoting (sla_ldr_pp.cu) for every factorisation -- a different pivot
+        // sequence than ?geqp3, hence a mode, never chosen by the dispatcher on its own
+        static const bool panel_mode = [] { const char* e = getenv("SLA_LDR_PIVOT"); return e && e[0] == 'p'; }();
         // Cluster kernels minimise latency (one matrix per CS SMs, ~132/CS matrices in flight), the streaming
         // kernel maximises throughput (one matrix per SM, 148 in flight) but is ~4x (register kernel) / ~2.5x
         // (shared-memory cluster kernel) slower per wave (profiles/ldr_kernels_r1.txt): pick by wave count.
@@ -196,7 +199,8 @@ template <typename T> struct Ctx {
             if (forced == 6) cs_mc = (mc_forced_cs == 2 || mc_forced_cs == 4 || mc_forced_cs == 8) ? mc_forced_cs : 4;
         }
         int algo;
-        if (forced == 6) { if (cs_mc == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_MULTICTA; }
+        if (forced == 7 || (forced == 0 && panel_mode)) { if (!ldr_pp_supported<T>(n)) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_PANEL; }
+        else if (forced == 6) { if (cs_mc == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_MULTICTA; }
         else if (forced == 0 && mc_on && n > 512 && cs_mc > 0) algo = SLA_LDR_ALGO_MULTICTA;
         else if (forced == 5) { if (cs_blk == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_BLOCKED; }
         else if (forced == 0 && blk_on && cs_blk > 0) algo = SLA_LDR_ALGO_BLOCKED;
@@ -210,6 +214,7 @@ template <typename T> struct Ctx {
         else algo = SLA_LDR_ALGO_STREAMING;
         a.info = w.info;
         switch (algo) {
+            case SLA_LDR_ALGO_PANEL: CK(ldr_pp_batched<T>(a, s)); break;
             case SLA_LDR_ALGO_MULTICTA: CK(ldr_mc_batched<T>(a, cs_mc, s)); break;
             case SLA_LDR_ALGO_BLOCKED: CK(ldr_blk_batched<T>(a, s)); break;
             case SLA_LDR_ALGO_HYBRID: CK(ldr_hyb_batched<T>(a, s)); break;

@@ -50,6 +50,9 @@ template <typename T> int ldr_blk_cluster_size(int n);
 // multi-CTA L2-streaming kernel for large n and small batches (sla_ldr_mc.cu): a cluster of cs CTAs per matrix, needs p.Qwork
 template <typename T> cudaError_t ldr_mc_batched(const LdrArgs<T>& p, int cs, cudaStream_t s);
 template <typename T> bool ldr_mc_supported(int n);
+// panel-restricted pivoting (sla_ldr_pp.cu): NOT the ?geqp3 pivot sequence -- the opt-in mode SLA_LDR_PIVOT=panel
+template <typename T> cudaError_t ldr_pp_batched(const LdrArgs<T>& p, cudaStream_t s);
+template <typename T> bool ldr_pp_supported(int n);
 // Q = H_0...H_{n-1} I on the FP64 tensor cores after a factorisation-only launch (real, n <= 256; taus in p.Twork)
 cudaError_t orgq_dmma_batched(const LdrArgs<double>& p, cudaStream_t s);
 
