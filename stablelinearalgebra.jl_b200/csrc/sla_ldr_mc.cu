@@ -306,12 +306,20 @@ __device__ void mc_panel_dot(T* __restrict__ Ws, const T* __restrict__ Ps, int l
         for (int j = 0; j < 4; ++j) { acc[j][0] = mk<T>(0.0); acc[j][1] = mk<T>(0.0); }
         // eight row steps per trip: all eight global loads of C are in flight before the first DMMA (one L2 round trip
         // per 32 rows instead of one per 4: this loop is latency-bound, profiles/ldr_stream_phases_r2.txt)
+        T cn[8];                                       // the NEXT trip's eight loads are issued before this trip's DMMAs
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = k_lo + 4 * u + fk;
+            cn[u] = (cvalid && r >= r_lo && r < r_hi) ? col[r] : mk<T>(0.0);
+        }
         for (int kk0 = k_lo; kk0 < r_hi; kk0 += 32) {
             T cf[8];
 #pragma unroll
+            for (int u = 0; u < 8; ++u) cf[u] = cn[u];
+#pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int r = kk0 + 4 * u + fk;
-                cf[u] = (cvalid && r >= r_lo && r < r_hi) ? col[r] : mk<T>(0.0);
+                const int r = kk0 + 32 + 4 * u + fk;
+                cn[u] = (cvalid && r >= r_lo && r < r_hi) ? col[r] : mk<T>(0.0);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
