@@ -15,6 +15,7 @@
 // Complex GEMM runs 4 real DMMAs per tile pair on the interleaved (re,im) data.
 #pragma once
 #include <atomic>
+#include <cstdlib>
 
 #include "sla_common.cuh"
 
@@ -97,6 +98,65 @@ template <typename T, bool IDXC, int BIDX, int BK> struct OperandTile {
     }
 };
 
+// Loader of the FAST instantiation (every tile full, 16-byte aligned rows): the per-thread chunk -> address map is
+// computed ONCE, before the k loop.  A thread's PER chunks of an operand tile are c = tid + i NT; when NT is a multiple
+// of the chunks per row they share one column offset and sit a fixed number of rows apart, so a k-tile costs
+// PER (64-bit add + LDGSTS with an immediate shared-memory offset) instead of the ~30 instructions of index / bounds /
+// zero-fill arithmetic per chunk of the general loader (measured round 2: 275 of the 490 instructions a warp issues
+// per k-tile were that arithmetic, profiles/gemm_fast_r2.txt).
+template <typename T, bool IDXC, int BIDX, int BK, int NT> struct FastLoader {
+    using Tile = OperandTile<T, IDXC, BIDX, BK>;
+    static constexpr int EPC = Tile::EPC, LD = Tile::LD;
+    static constexpr int CPR = (IDXC ? BIDX : BK) / EPC;      // 16-byte chunks per contiguous row of the tile
+    static constexpr int ROWS = IDXC ? BK : BIDX;
+    static constexpr int TOTAL = CPR * ROWS;
+    static constexpr bool OK = (TOTAL % NT == 0) && ((IDXC ? BIDX : BK) % EPC == 0);
+    static constexpr int PER = OK ? TOTAL / NT : 1;
+    static constexpr bool AFFINE = (NT % CPR == 0);
+    static constexpr int RSTEP = AFFINE ? NT / CPR : 0;       // rows between consecutive chunks of a thread
+
+    const char* g;                 // this thread's chunk 0 of the current k-tile
+    long long gstep, kstep;        // bytes between its consecutive chunks (AFFINE) / between k-tiles
+    unsigned s0;                   // shared-memory byte offset of chunk 0 inside the operand tile
+    int goff[AFFINE ? 1 : PER];    // !AFFINE: byte offsets of the chunks from g / inside the tile
+    unsigned soff[AFFINE ? 1 : PER];
+
+    // tile origin: global element (idx0, k = 0) of an operand with leading dimension ld
+    __device__ __forceinline__ void init(const T* base, int ld, int idx0, int tid) {
+        const long long row_b = (long long)ld * (long long)sizeof(T);
+        const T* origin = IDXC ? base + idx0 : base + (long long)idx0 * ld;
+        kstep = IDXC ? row_b * BK : (long long)BK * (long long)sizeof(T);
+        if constexpr (AFFINE) {
+            const int r = tid / CPR, cc = tid % CPR;
+            g = reinterpret_cast<const char*>(origin) + r * row_b + (long long)cc * 16;
+            gstep = row_b * RSTEP;
+            s0 = (unsigned)((r * LD + cc * EPC) * (int)sizeof(T));
+        } else {
+            g = reinterpret_cast<const char*>(origin);
+            gstep = 0; s0 = 0;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int c = tid + i * NT, r = c / CPR, cc = c % CPR;
+                goff[i] = (int)(r * row_b) + cc * 16;
+                soff[i] = (unsigned)((r * LD + cc * EPC) * (int)sizeof(T));
+            }
+        }
+    }
+    // issue the copies of the current k-tile into the tile at shared address `stile`, then step to the next k-tile
+    __device__ __forceinline__ void issue(unsigned stile) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            if constexpr (AFFINE) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stile + s0 + (unsigned)(i * RSTEP * LD * (int)sizeof(T))),
+                             "l"(g + i * gstep));
+            } else {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stile + soff[i]), "l"(g + goff[i]));
+            }
+        }
+        g += kstep;
+    }
+};
+
 // acc(8x8 tile pair) += nfrag (x) mfrag
 __device__ __forceinline__ void mma_tile(double (&acc)[2], double nf, double mf) { dmma884(acc[0], acc[1], nf, mf); }
 __device__ __forceinline__ void mma_tile(cplx (&acc)[2], cplx nf, cplx mf) {
@@ -106,7 +166,7 @@ __device__ __forceinline__ void mma_tile(cplx (&acc)[2], cplx nf, cplx mf) {
     dmma884(acc[0].im, acc[1].im, nf.im, mf.re);
 }
 
-template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES, bool VEC>
+template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES, bool VEC, bool FAST = false>
 // 64x64 real tiles: cap the registers at 128 so that 4 CTAs (not 3) are resident per SM -- fewer, fuller waves for the
 // 1024-2048 CTA launches of a 64-128 chain batch
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (sizeof(T) == 8 && BM * BN <= 64 * 64) ? 4 : 1) gemm_kernel(GemmArgs<T> p) {
@@ -163,14 +223,29 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (sizeof(T) == 8 &&
     }
 
     const int KT = (p.K + BK - 1) / BK;
+    using FastA = FastLoader<T, OPA == OP_N, BM, BK, NT>;
+    using FastB = FastLoader<T, OPB == OP_C, BN, BK, NT>;
+    FastA fla;
+    FastB flb;
+    const unsigned smem_base = smem_u32(smem);
+    if constexpr (FAST) {
+        fla.init(A, p.lda, m0, tid);
+        flb.init(B, p.ldb, n0, tid);
+    }
     auto load_stage = [&](int stage, int kt) {
 #ifdef SLA_GEMM_ABLATE_LOADS   // timing experiment only (wrong results): no global->shared traffic after the prologue
         if (kt >= STAGES - 1) return;
 #endif
-        T* sa = smem + stage * STAGE_ELEMS;
-        T* sb = sa + TileA::ELEMS;
-        TileA::template load<NT, VEC>(sa, A, p.lda, m0, kt * BK, p.M, p.K, tid);
-        TileB::template load<NT, VEC>(sb, B, p.ldb, n0, kt * BK, p.N, p.K, tid);
+        if constexpr (FAST) {   // k-tiles are requested in order: the loaders carry the running pointers
+            const unsigned st = smem_base + (unsigned)(stage * STAGE_ELEMS * (int)sizeof(T));
+            fla.issue(st);
+            flb.issue(st + (unsigned)(TileA::ELEMS * (int)sizeof(T)));
+        } else {
+            T* sa = smem + stage * STAGE_ELEMS;
+            T* sb = sa + TileA::ELEMS;
+            TileA::template load<NT, VEC>(sa, A, p.lda, m0, kt * BK, p.M, p.K, tid);
+            TileB::template load<NT, VEC>(sb, B, p.ldb, n0, kt * BK, p.N, p.K, tid);
+        }
     };
 
 #pragma unroll
@@ -264,13 +339,13 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, (sizeof(T) == 8 &&
     }
 }
 
-template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES, bool VEC>
+template <typename T, int OPA, int OPB, int BM, int BN, int WM, int WN, int BK, int STAGES, bool VEC, bool FAST = false>
 static cudaError_t launch_gemm_vec(const GemmArgs<T>& p, cudaStream_t stream) {
     using TileA = OperandTile<T, OPA == OP_N, BM, BK>;
     using TileB = OperandTile<T, OPB == OP_C, BN, BK>;
     constexpr int SMEM = STAGES * (TileA::ELEMS + TileB::ELEMS) * (int)sizeof(T);
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
-    auto kern = gemm_kernel<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES, VEC>;
+    auto kern = gemm_kernel<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES, VEC, FAST>;
     // the attribute is per device (context): cached per instantiation AND device ordinal
     static bool configured[kMaxDevices] = {};
     const int dev = current_device();
@@ -293,6 +368,13 @@ static cudaError_t launch_gemm_cfg(const GemmArgs<T>& p, cudaStream_t stream) {
     if (sizeof(T) == 8)
         vec = ((p.lda & 1) == 0) && ((p.ldb & 1) == 0) && ((p.strideA & 1) == 0) && ((p.strideB & 1) == 0) &&
               ((((uintptr_t)p.A) & 15) == 0) && ((((uintptr_t)p.B) & 15) == 0);
+    constexpr int NT = (BM / WM) * (BN / WN) * 32;
+    if constexpr (FastLoader<T, OPA == OP_N, BM, BK, NT>::OK && FastLoader<T, OPB == OP_C, BN, BK, NT>::OK) {
+        // every tile full and every row 16-byte aligned: the loader with precomputed addresses
+        static const bool fast_off = getenv("SLA_GEMM_FAST") && atoi(getenv("SLA_GEMM_FAST")) == 0;   // A/B experiments
+        if (vec && !fast_off && p.M % BM == 0 && p.N % BN == 0 && p.K % BK == 0 && p.K >= BK)
+            return launch_gemm_vec<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES, true, true>(p, stream);
+    }
     if (vec) return launch_gemm_vec<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES, true>(p, stream);
     return launch_gemm_vec<T, OPA, OPB, BM, BN, WM, WN, BK, STAGES, false>(p, stream);
 }
