@@ -39,28 +39,34 @@ constexpr int OQ_RING = 2 * 8 * OQ_LDV;
 // fi, 16 bytes each) AND the update sweep (lanes = reflector 2 fk + kk, 8 consecutive rows) both need the minimal
 // number of wavefronts (the update sweep is 4-way conflicted without it).
 __device__ __forceinline__ int oq_swz(int j) { return ((j >> 1) & 1) << 3; }
-// ring | partial Z^T [8 warps][8 groups][32 lanes][2] | T of every chunk [32][64] | scratch [8 warps][64] | Y^T [8 groups][32][2] | taus
-constexpr size_t OQ_SMEM = (size_t)(OQ_RING + 8 * 8 * 64 + 32 * 64 + 8 * 64 + 8 * 64 + 256) * sizeof(double) + 64;
+// ring | partial Z^T [8 warps][NG groups][32 lanes][2] | T of every chunk [32][64] | scratch [8 warps][64] | Y^T [NG groups][32][2] | taus
+template <int NG> constexpr size_t oq_smem() { return (size_t)(OQ_RING + 8 * NG * 64 + 32 * 64 + 8 * 64 + NG * 64 + 256) * sizeof(double) + 64; }
 
 // ROW-DISTRIBUTED: warp w owns the row blocks s = w, w+8, w+16, w+24 (8 rows each) of ALL 64 columns of its CTA
 // (8 column groups).  A V fragment is then loaded once per row block and used for every column group (a warp that
 // owns columns re-reads the whole chunk of V: that version was bound by shared-memory traffic and by the barrier
 // imbalance between heavy and light column groups), the dead rows (< k0) are shed evenly by all warps, and the
 // price is one reduction of the partial Z^T through shared memory per chunk (warp g finishes column group g).
-__global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double> p) {
+//
+// NG = column groups per CTA (8 columns each): NG = 8 -> a cluster of 4 CTAs per matrix, one CTA per SM (Q = 128 registers
+// per lane); NG = 4 -> a cluster of 8 CTAs with half the columns each, TWO CTAs resident per SM, so that one CTA's
+// per-chunk barriers and shared-memory round trips overlap with the other's tensor-core work.
+template <int NG>
+__global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(LdrArgs<double> p) {
+    constexpr int CS = 32 / NG;   // CTAs per matrix; column c = CS (8 g + fi) + rank
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* const ring = reinterpret_cast<double*>(smem_raw);   // [2][8][OQ_LDV]
     double* const Zp = ring + OQ_RING;                          // [8 warps][8 groups][32 lanes][2]
-    double* const Tall = Zp + 8 * 8 * 64;                       // [32 chunks][64]  T of every chunk (row-major)
+    double* const Tall = Zp + 8 * NG * 64;                      // [32 chunks][64]  T of every chunk (row-major)
     double* const Tw = Tall + 32 * 64;                          // [8 warps][64]  scratch of the T prologue
     double* const Ys = Tw + 8 * 64;                             // [8 groups][32 lanes][2]
-    double* const taus = Ys + 8 * 64;                           // [256]
+    double* const taus = Ys + NG * 64;                          // [256]
 
     const int n = p.n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fi = lane >> 2, fk = lane & 3;
     const int rank = (int)cg::this_cluster().block_rank();
-    const int b = blockIdx.x / 4;
+    const int b = blockIdx.x / CS;
     double* Lg = p.L + (long long)b * p.strideL;
     const int ldl = p.ldl;
     const double* tau_g = p.Twork + (long long)b * p.strideT;
@@ -69,10 +75,10 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
     for (int r = tid; r < OQ_RING; r += OQ_THREADS) ring[r] = 0.0;   // rows >= n stay zero for ever
 
     // lane (fi, fk) holds Q[row = 8 (warp + 8 i) + 2 fk + e][col = 32 g + 4 fi + rank]
-    double Qt[8][4][2];
+    double Qt[NG][4][2];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const int c = 32 * g + 4 * fi + rank;
+    for (int g = 0; g < NG; ++g) {
+        const int c = CS * (8 * g + fi) + rank;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = 8 * (warp + 8 * i) + 2 * fk;
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
         if (ch > 0) load_chunk(ch - 1, (ch - 1) & 1);
         const double* vb = ring + (size_t)(ch & 1) * 8 * OQ_LDV;
         const int k0 = ch * 8, kcnt = min(8, n - k0), s0 = ch;   // rows < k0 = 8 s0 are zero in every reflector of the chunk
-        const int g0 = k0 >> 5;                                  // column groups < g0 lie left of the chunk: untouched
+        const int g0 = k0 / (8 * CS);                            // column groups < g0 lie left of the chunk: untouched
         // reflector j of the chunk, row k0 + r8 (only block s0 needs the mask): 0 above the diagonal, 1 on it
         auto masked = [&](double raw, int j, int r8) { return (r8 < j) ? 0.0 : (r8 == j ? 1.0 : raw); };
         const bool jx_fi = fi < kcnt;                            // reflector fi exists
@@ -152,9 +158,9 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
 
         // ---- partial Z^T over this warp's live row blocks
         {
-            double z[8][2];
+            double z[NG][2];
 #pragma unroll
-            for (int g = 0; g < 8; ++g) { z[g][0] = 0.0; z[g][1] = 0.0; }
+            for (int g = 0; g < NG; ++g) { z[g][0] = 0.0; z[g][1] = 0.0; }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int sb = warp + 8 * i;
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
                     if (sb == s0) { vv.x = masked(vv.x, fi, 2 * fk); vv.y = masked(vv.y, fi, 2 * fk + 1); }
                     if (!jx_fi) { vv.x = 0.0; vv.y = 0.0; }
 #pragma unroll
-                    for (int g = 0; g < 8; ++g)
+                    for (int g = 0; g < NG; ++g)
                         if (g >= g0) {
                             dmma884(z[g][0], z[g][1], Qt[g][i][0], vv.x);   // Z^T[col = fi][j = 2 fk + e]
                             dmma884(z[g][0], z[g][1], Qt[g][i][1], vv.y);
@@ -171,18 +177,18 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
                 }
             }
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-                if (g >= g0) *reinterpret_cast<double2*>(Zp + ((size_t)(warp * 8 + g) * 32 + lane) * 2) = make_double2(z[g][0], z[g][1]);
+            for (int g = 0; g < NG; ++g)
+                if (g >= g0) *reinterpret_cast<double2*>(Zp + ((size_t)(warp * NG + g) * 32 + lane) * 2) = make_double2(z[g][0], z[g][1]);
         }
         __syncthreads();
 
         // ---- warp g finishes column group g: Z^T = sum of the partials, T, Y^T = Z^T T^T
-        if (warp >= g0) {
+        if (warp >= g0 && warp < NG) {
             const double* const Tm = Tall + ch * 64;   // from the prologue
             double z0 = 0.0, z1 = 0.0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-                const double2 zp = *reinterpret_cast<const double2*>(Zp + ((size_t)(w * 8 + warp) * 32 + lane) * 2);
+                const double2 zp = *reinterpret_cast<const double2*>(Zp + ((size_t)(w * NG + warp) * 32 + lane) * 2);
                 z0 += zp.x; z1 += zp.y;
             }
             // Y^T = Z^T T^T   (k slot (fk, kk) <-> i = 2 fk + kk: the fragment as it came out)
@@ -196,9 +202,9 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
 
         // ---- Q^T -= Y^T V^T on this warp's live row blocks, every live column group (k slot <-> j = 2 fk + kk)
         {
-            double ny[8][2];
+            double ny[NG][2];
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
+            for (int g = 0; g < NG; ++g)
                 if (g >= g0) {
                     const double2 y2 = *reinterpret_cast<const double2*>(Ys + ((size_t)g * 32 + lane) * 2);
                     ny[g][0] = y2.x; ny[g][1] = y2.y;
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
                     if (!ja) b0 = 0.0;
                     if (!jb) b1 = 0.0;
 #pragma unroll
-                    for (int g = 0; g < 8; ++g)
+                    for (int g = 0; g < NG; ++g)
                         if (g >= g0) {
                             dmma884(Qt[g][i][0], Qt[g][i][1], ny[g][0], b0);
                             dmma884(Qt[g][i][0], Qt[g][i][1], ny[g][1], b1);
@@ -227,8 +233,8 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
     {
         const bool v2 = (((size_t)ldl * sizeof(double)) % 16 == 0) && ((((uintptr_t)Lg) & 15) == 0);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const int c = 32 * g + 4 * fi + rank;
+        for (int g = 0; g < NG; ++g) {
+            const int c = CS * (8 * g + fi) + rank;
             if (c >= n) continue;
             double* dst = Lg + (long long)c * ldl;
 #pragma unroll
@@ -246,32 +252,40 @@ __global__ void __launch_bounds__(OQ_THREADS, 1) orgq_dmma_kernel(LdrArgs<double
 
 }  // namespace
 
-// Q formation for real matrices with n <= 256 after a MODE 1 launch of ldr_reg_kernel (taus in p.Twork)
-cudaError_t orgq_dmma_batched(const LdrArgs<double>& p, cudaStream_t stream) {
-    if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
-    if (p.n > 256 || p.Twork == nullptr || p.strideT < p.n) return cudaErrorNotSupported;
+template <int NG> static cudaError_t launch_orgq(const LdrArgs<double>& p, cudaStream_t stream) {
+    constexpr int CS = 32 / NG;
     static bool configured[kMaxDevices] = {};   // the attribute is per device
     const int dev = current_device();
     if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(orgq_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OQ_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(orgq_dmma_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)oq_smem<NG>());
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)p.batch * 4, 1, 1);
+    cfg.gridDim = dim3((unsigned)p.batch * CS, 1, 1);
     cfg.blockDim = dim3(OQ_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = OQ_SMEM;
+    cfg.dynamicSmemBytes = oq_smem<NG>();
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.x = CS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, orgq_dmma_kernel, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, orgq_dmma_kernel<NG>, p);
     ++g_launch_count;
     return e;
+}
+
+// Q formation for real matrices with n <= 256 after a MODE 1 launch of ldr_reg_kernel (taus in p.Twork)
+cudaError_t orgq_dmma_batched(const LdrArgs<double>& p, cudaStream_t stream) {
+    if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
+    if (p.n > 256 || p.Twork == nullptr || p.strideT < p.n) return cudaErrorNotSupported;
+    // SLA_ORGQ_NG=4: clusters of 8 CTAs with 32 columns each, two CTAs per SM (A/B experiments)
+    static const int ng = getenv("SLA_ORGQ_NG") ? atoi(getenv("SLA_ORGQ_NG")) : 8;
+    if (ng == 4) return launch_orgq<4>(p, stream);
+    return launch_orgq<8>(p, stream);
 }
 
 }  // namespace sla
