@@ -715,6 +715,12 @@ int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const
             T*& XR2 = intoU ? UR2 : FR2;
             double* Xd = intoU ? Ud : Fd;
             const T* Bg = fin + (long long)gg * batch * nn;
+            if (g == 0 || (intoU && g == half)) {
+                // the state is still the identity: (B I) 1 = B and R0 I = R0 bit for bit, so the two GEMMs of lmul! are
+                // skipped -- ldr! reads B_bar directly and writes R0 where R lives
+                CKI(c.ldr(XL, Xd, XR, Bg, nn));
+                continue;
+            }
             CKI(c.gemm(c.w.M, OP_N, Bg, nn, OP_N, XL, nn, nullptr, SCALE_NONE, Xd, SCALE_MUL));
             CKI(c.ldr(XL, Xd, c.w.Mp, c.w.M, nn));
             CKI(c.gemm(XR2, OP_N, c.w.Mp, nn, OP_N, XR, nn));

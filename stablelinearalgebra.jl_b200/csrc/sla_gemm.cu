@@ -26,6 +26,9 @@ template <typename T, int OPA, int OPB> static cudaError_t gemm_pick_tile(const 
         if (force_tile == 128) return launch_gemm_cfg<T, OPA, OPB, 128, 128, 64, 32, 16, 3>(p, s);
         auto padded = [&](int t) { return (long long)((p.M + t - 1) / t) * ((p.N + t - 1) / t) * t * t; };
         if (padded(80) * 10 < padded(64) * 9) return launch_gemm_cfg<T, OPA, OPB, 80, 80, 40, 40, 16, 3>(p, s);
+        // full 64x64x16 tiles run the precomputed-address loader: two stages are enough to cover the L2 latency there
+        // (31.4 vs 31.2 TFLOP/s at batch 128, 33.6 vs 33.4 at batch 1280, C2 step -0.1 ms: profiles/gemm_fast_r2.txt)
+        if (p.M % 64 == 0 && p.N % 64 == 0 && p.K % 16 == 0) return launch_gemm_cfg<T, OPA, OPB, 64, 64, 32, 32, 16, 2>(p, s);
         return launch_gemm_cfg<T, OPA, OPB, 64, 64, 32, 32, 16, 3>(p, s);
     }
 }

@@ -86,21 +86,29 @@ __global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(
             Qt[g][i][1] = (r + 1 == c && c < n) ? 1.0 : 0.0;
         }
     }
-    __syncthreads();
+    cg::this_cluster().sync();   // taus / ring are set, and every CTA of the cluster runs: its shared memory may be written
 
     const int nchunk = (n + 7) / 8;
-    // ---- prologue: T of EVERY chunk (they depend on V only), four chunks per warp, straight from global memory:
-    // G = V^T V on the tensor core, then the ?larft recurrence on 8 lanes -- off the per-chunk critical path
-    for (int cq = warp; cq < nchunk; cq += 8) {
+    // ---- prologue: T of EVERY chunk (they depend on V only), straight from global memory: G = V^T V on the tensor
+    // core, then the ?larft recurrence on 8 lanes -- off the per-chunk critical path.  The chunks are shared out over the
+    // CTAs of the cluster (chunk cq -> CTA cq % CS, warp cq / CS) and each T is written into every CTA's shared memory
+    // (DSMEM stores): a warp builds at most one or two T instead of four.
+    for (int cq = rank + CS * warp; cq < nchunk; cq += CS * 8) {
         const int k0 = cq * 8, kj = k0 + fi;           // lane's reflector (column kj of L)
         const double* col = Lg + (long long)kj * ldl;
         double g0a = 0.0, g1a = 0.0, g0b = 0.0, g1b = 0.0;
-        for (int t = 2 * cq; t < 64; t += 2) {         // two independent accumulation chains
-            const int r0 = 4 * t + fk, r1 = r0 + 4;
-            double x0 = (kj < n && r0 < n && r0 > kj) ? col[r0] : ((r0 == kj && kj < n) ? 1.0 : 0.0);
-            double x1 = (kj < n && r1 < n && r1 > kj) ? col[r1] : ((r1 == kj && kj < n) ? 1.0 : 0.0);
-            dmma884(g0a, g1a, x0, x0);                 // G[j = fi][j' = 2 fk + e]
-            dmma884(g0b, g1b, x1, x1);
+        for (int t = 2 * cq; t < 64; t += 8) {         // eight loads in flight, two independent accumulation chains
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = 4 * (t + u) + fk;
+                x[u] = (kj < n && r < n && r > kj) ? col[r] : ((r == kj && kj < n) ? 1.0 : 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                dmma884(g0a, g1a, x[u], x[u]);         // G[j = fi][j' = 2 fk + e]
+                dmma884(g0b, g1b, x[u + 1], x[u + 1]);
+            }
         }
         double* const Gm = Tw + warp * 64;
         Gm[fi * 8 + 2 * fk] = g0a + g0b;
@@ -122,11 +130,15 @@ __global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(
                     Trow[j] = -taus[k0 + j] * acc;
                 }
             }
+            for (int pr = 0; pr < CS; ++pr) {
+                double* const Tpeer = cg::this_cluster().map_shared_rank(Tall, pr);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) Tall[cq * 64 + i * 8 + j] = Trow[j];
+                for (int j = 0; j < 8; ++j) Tpeer[cq * 64 + i * 8 + j] = Trow[j];
+            }
         }
         __syncwarp();
     }
+    cg::this_cluster().sync();   // every T has arrived
     const bool vecq = (((size_t)ldl * sizeof(double)) % 16 == 0) && ((((uintptr_t)Lg) & 15) == 0) && (n % 2 == 0);
     auto load_chunk = [&](int ch, int buf) {   // 32 threads per reflector
         const int i = tid >> 5, k = ch * 8 + i;
@@ -282,10 +294,12 @@ template <int NG> static cudaError_t launch_orgq(const LdrArgs<double>& p, cudaS
 cudaError_t orgq_dmma_batched(const LdrArgs<double>& p, cudaStream_t stream) {
     if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
     if (p.n > 256 || p.Twork == nullptr || p.strideT < p.n) return cudaErrorNotSupported;
-    // SLA_ORGQ_NG=4: clusters of 8 CTAs with 32 columns each, two CTAs per SM (A/B experiments)
-    static const int ng = getenv("SLA_ORGQ_NG") ? atoi(getenv("SLA_ORGQ_NG")) : 8;
-    if (ng == 4) return launch_orgq<4>(p, stream);
-    return launch_orgq<8>(p, stream);
+    // default: clusters of 8 CTAs with 32 columns each, two CTAs per SM -- 0.178 vs 0.190 ms alone for 64 x N=256, and
+    // 32.24 vs 32.61 ms per C2 step (the half-size CTAs interleave with the side-stream GEMM CTAs; gpurun_out/r2_orgq_ng.log).
+    // SLA_ORGQ_NG=8: clusters of 4 CTAs with 64 columns each, one CTA per SM (round 1)
+    static const int ng = getenv("SLA_ORGQ_NG") ? atoi(getenv("SLA_ORGQ_NG")) : 4;
+    if (ng == 8) return launch_orgq<8>(p, stream);
+    return launch_orgq<4>(p, stream);
 }
 
 }  // namespace sla
