@@ -34,7 +34,8 @@ namespace {
 constexpr int OQ_THREADS = 256;   // 8 warps
 constexpr int OQ_LDV = 264;       // row stride of a reflector in the ring: = 8 (mod 16) doubles -> the 16-byte B loads of
                                   // the Z sweep are bank-conflict free
-constexpr int OQ_RING = 2 * 8 * OQ_LDV;
+constexpr int OQ_NBUF = 3;       // chunks of reflectors in the ring
+constexpr int OQ_RING = OQ_NBUF * 8 * OQ_LDV;
 // Row swizzle of the ring: reflectors 2,3,6,7 of a chunk store row r at r ^ 8, so that the Z sweep (lanes = reflector
 // fi, 16 bytes each) AND the update sweep (lanes = reflector 2 fk + kk, 8 consecutive rows) both need the minimal
 // number of wavefronts (the update sweep is 4-way conflicted without it).
@@ -55,7 +56,7 @@ template <int NG>
 __global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(LdrArgs<double> p) {
     constexpr int CS = 32 / NG;   // CTAs per matrix; column c = CS (8 g + fi) + rank
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* const ring = reinterpret_cast<double*>(smem_raw);   // [2][8][OQ_LDV]
+    double* const ring = reinterpret_cast<double*>(smem_raw);   // [OQ_NBUF][8][OQ_LDV]
     double* const Zp = ring + OQ_RING;                          // [8 warps][8 groups][32 lanes][2]
     double* const Tall = Zp + 8 * NG * 64;                      // [32 chunks][64]  T of every chunk (row-major)
     double* const Tw = Tall + 32 * 64;                          // [8 warps][64]  scratch of the T prologue
@@ -86,17 +87,24 @@ __global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(
             Qt[g][i][1] = (r + 1 == c && c < n) ? 1.0 : 0.0;
         }
     }
-    cg::this_cluster().sync();   // taus / ring are set, and every CTA of the cluster runs: its shared memory may be written
+    // The three cluster-wide barriers of this kernel are split into arrive / wait so that their latency hides behind work
+    // that does not depend on them (round 2: 10 % of the stall samples sat in cluster.sync()).
+    auto cl_arrive = [] { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); };
+    auto cl_wait = [] { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); };
+    cl_arrive();   // #1: taus / ring are set (also the CTA-wide barrier for them) and this CTA runs
 
     const int nchunk = (n + 7) / 8;
     // ---- prologue: T of EVERY chunk (they depend on V only), straight from global memory: G = V^T V on the tensor
     // core, then the ?larft recurrence on 8 lanes -- off the per-chunk critical path.  The chunks are shared out over the
     // CTAs of the cluster (chunk cq -> CTA cq % CS, warp cq / CS) and each T is written into every CTA's shared memory
     // (DSMEM stores): a warp builds at most one or two T instead of four.
-    for (int cq = rank + CS * warp; cq < nchunk; cq += CS * 8) {
-        const int k0 = cq * 8, kj = k0 + fi;           // lane's reflector (column kj of L)
+    // (n <= 256: at most 32 chunks over CS x 8 warps -- one chunk per warp, or none)
+    const int cq = rank + CS * warp;
+    const bool has_t = cq < nchunk;
+    double g0a = 0.0, g1a = 0.0, g0b = 0.0, g1b = 0.0;
+    if (has_t) {
+        const int kj = cq * 8 + fi;                    // lane's reflector (column kj of L)
         const double* col = Lg + (long long)kj * ldl;
-        double g0a = 0.0, g1a = 0.0, g0b = 0.0, g1b = 0.0;
         for (int t = 2 * cq; t < 64; t += 8) {         // eight loads in flight, two independent accumulation chains
             double x[8];
 #pragma unroll
@@ -110,6 +118,10 @@ __global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(
                 dmma884(g0b, g1b, x[u + 1], x[u + 1]);
             }
         }
+    }
+    cl_wait();     // #1: every CTA of the cluster runs (its shared memory may be written); taus visible
+    if (has_t) {
+        const int k0 = cq * 8;
         double* const Gm = Tw + warp * 64;
         Gm[fi * 8 + 2 * fk] = g0a + g0b;
         Gm[fi * 8 + 2 * fk + 1] = g1a + g1b;
@@ -138,7 +150,7 @@ __global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(
         }
         __syncwarp();
     }
-    cg::this_cluster().sync();   // every T has arrived
+    cl_arrive();   // #2: this CTA's T blocks are written everywhere
     const bool vecq = (((size_t)ldl * sizeof(double)) % 16 == 0) && ((((uintptr_t)Lg) & 15) == 0) && (n % 2 == 0);
     auto load_chunk = [&](int ch, int buf) {   // 32 threads per reflector
         const int i = tid >> 5, k = ch * 8 + i;
@@ -153,13 +165,18 @@ __global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(
         }
         cp_async_commit();
     };
-    load_chunk(nchunk - 1, (nchunk - 1) & 1);
+    // Three-buffer ring, two barriers per chunk: chunk ch - 2 is requested after the first barrier of chunk ch (everybody
+    // has left the update of chunk ch + 1, the previous user of that buffer) and awaited before the second barrier of
+    // chunk ch - 1, so a warp runs from its update of chunk ch straight into its partial Z of chunk ch - 1.
+    load_chunk(nchunk - 1, (nchunk - 1) % OQ_NBUF);
+    if (nchunk >= 2) load_chunk(nchunk - 2, (nchunk - 2) % OQ_NBUF); else cp_async_commit();
+    cp_async_wait<1>();
+    cl_wait();         // #2: every T has arrived
+    __syncthreads();   // chunk nchunk - 1 has landed for everybody
 
     for (int ch = nchunk - 1; ch >= 0; --ch) {
-        cp_async_wait<0>();
-        __syncthreads();   // chunk ch has landed; everybody is done with chunk ch + 1 (the other buffer, Zp, Ys)
-        if (ch > 0) load_chunk(ch - 1, (ch - 1) & 1);
-        const double* vb = ring + (size_t)(ch & 1) * 8 * OQ_LDV;
+        if (ch == 0) cl_arrive();   // #3: all of this CTA's reads of the reflectors in L have completed
+        const double* vb = ring + (size_t)(ch % OQ_NBUF) * 8 * OQ_LDV;
         const int k0 = ch * 8, kcnt = min(8, n - k0), s0 = ch;   // rows < k0 = 8 s0 are zero in every reflector of the chunk
         const int g0 = k0 / (8 * CS);                            // column groups < g0 lie left of the chunk: untouched
         // reflector j of the chunk, row k0 + r8 (only block s0 needs the mask): 0 above the diagonal, 1 on it
@@ -192,7 +209,8 @@ __global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(
             for (int g = 0; g < NG; ++g)
                 if (g >= g0) *reinterpret_cast<double2*>(Zp + ((size_t)(warp * NG + g) * 32 + lane) * 2) = make_double2(z[g][0], z[g][1]);
         }
-        __syncthreads();
+        __syncthreads();   // partial Z^T written; everybody has left the update of chunk ch + 1
+        if (ch >= 2) load_chunk(ch - 2, (ch - 2) % OQ_NBUF); else cp_async_commit();
 
         // ---- warp g finishes column group g: Z^T = sum of the partials, T, Y^T = Z^T T^T
         if (warp >= g0 && warp < NG) {
@@ -210,7 +228,8 @@ __global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(
             dmma884(y0, y1, z1, t2.y);
             *reinterpret_cast<double2*>(Ys + ((size_t)warp * 32 + lane) * 2) = make_double2(-y0, -y1);
         }
-        __syncthreads();
+        cp_async_wait<1>();   // this thread's part of chunk ch - 1 (requested one chunk ago) has landed
+        __syncthreads();      // Y^T written; chunk ch - 1 visible to everybody
 
         // ---- Q^T -= Y^T V^T on this warp's live row blocks, every live column group (k slot <-> j = 2 fk + kk)
         {
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(OQ_THREADS, NG == 8 ? 1 : 2) orgq_dmma_kernel(
             }
         }
     }
-    cg::this_cluster().sync();   // every CTA of the matrix is done reading the reflectors from L
+    cl_wait();   // #3: every CTA of the matrix is done reading the reflectors from L
 
     {
         const bool v2 = (((size_t)ldl * sizeof(double)) % 16 == 0) && ((((uintptr_t)Lg) & 15) == 0);
