@@ -23,6 +23,7 @@ struct sla_handle_s {
     // fused driver only: a lower-priority side stream on which the group products (independent of the chain
     // state) are built while the chain's latency-bound LDR kernels leave SMs idle; created lazily
     cudaStream_t side = nullptr;
+    cudaStream_t side_more[3] = {};   // further side streams: consecutive sub-chunks of group products go round-robin over them
     cudaEvent_t ev_start = nullptr;
     cudaEvent_t ev_chunk[64] = {};
     int n_events = 0;
@@ -631,6 +632,7 @@ static int ensure_side_stream(sla_handle_t h) {
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));
+    for (int i = 0; i < 3; ++i) CK(cudaStreamCreateWithPriority(&h->side_more[i], cudaStreamNonBlocking, lo));
     CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
     for (int i = 0; i < 64; ++i) CK(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
     h->n_events = 64;
@@ -664,16 +666,23 @@ int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const
     // sub-chunks on a side stream and the chain waits per sub-chunk, so that GEMM CTAs fill the SMs the
     // cluster LDR kernels cannot use.
     static const bool overlap = [] { const char* e = getenv("SLA_OVERLAP"); return !(e && e[0] == '0'); }();
-    static const int SUB = [] { const char* e = getenv("SLA_OVERLAP_SUB"); int v = e ? atoi(e) : 2; return v > 0 ? v : 2; }();   // groups per sub-chunk
+    static const int SUB0 = [] { const char* e = getenv("SLA_OVERLAP_SUB"); int v = e ? atoi(e) : 1; return v > 0 ? v : 1; }();   // groups per sub-chunk
+    // measured on the C2 step (gpurun_out/r2_sides.log): 1 stream x 2 groups 31.69 ms, 2 streams x 1 group 31.43, 2 x 2 32.27,
+    // 3 x 1 32.11, 4 x 1 32.62 -- small low-priority launches leave the SMs to the chain's cluster kernels sooner
     if (overlap) CKI(ensure_side_stream(h));
     for (int g0 = 0; g0 < ng; g0 += gc) {
         const int gcur = (ng - g0 < gc) ? (ng - g0) : gc;
+        const int SUB = SUB0 > (gcur + 63) / 64 ? SUB0 : (gcur + 63) / 64;   // at most 64 sub-chunks (events) per pass
         const int nsub = (gcur + SUB - 1) / SUB;
         const bool ov = overlap && nsub <= 64;
+        // Consecutive sub-chunks are independent of each other: they go round-robin over SLA_SIDES (default 2) side streams so that the
+        // partial last wave of one sub-chunk's GEMM launches is filled by the other's (SLA_SIDES=1: one side stream).
+        // The second stream starts after sub-chunk 0, which the chain is waiting for, has the GPU to itself.
+        static const int n_sides = [] { const char* e = getenv("SLA_SIDES"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
         cudaStream_t bs = ov ? h->side : s;
         if (ov) {
             CK(cudaEventRecord(h->ev_start, s));          // the buffers' previous consumers / exp(lam s) are done
-            CK(cudaStreamWaitEvent(bs, h->ev_start, 0));
+            CK(cudaStreamWaitEvent(h->side, h->ev_start, 0));
         }
         // X_1 = diag(e_1) expK ; X_i = diag(e_i) (expK X_{i-1})      (test/runtests.jl:93-100)
         // group-major layout: product of (group gg, chain c) lives at index gg*batch + c
@@ -681,6 +690,11 @@ int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const
         for (int sc = 0; sc < nsub; ++sc) {
             const int ga = sc * SUB, gb = (ga + SUB < gcur) ? ga + SUB : gcur;
             T *cur = cw.B0, *nxt = cw.B1;
+            if (ov && n_sides > 1 && nsub > 2) {
+                const int si = sc % n_sides;
+                bs = si == 0 ? h->side : h->side_more[si - 1];
+                if (sc >= 1 && sc < n_sides) CK(cudaStreamWaitEvent(bs, h->ev_chunk[0], 0));   // (ev_chunk[0] follows ev_start)
+            }
             for (int i = 0; i < n_stab; ++i) {
                 const double* rs0 = cw.ev + ((long long)(g0 + ga) * n_stab + i) * n;
                 if (i == 0) {
@@ -938,6 +952,7 @@ int sla_destroy(sla_handle_t handle) {
         for (auto& e : handle->graphs)
             if (e.exec) cudaGraphExecDestroy(e.exec);
         if (handle->side) cudaStreamDestroy(handle->side);
+        for (int i = 0; i < 3; ++i) if (handle->side_more[i]) cudaStreamDestroy(handle->side_more[i]);
         if (handle->ev_start) cudaEventDestroy(handle->ev_start);
         for (int i = 0; i < handle->n_events; ++i) cudaEventDestroy(handle->ev_chunk[i]);
     }
