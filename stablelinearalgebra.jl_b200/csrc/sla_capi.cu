@@ -3,6 +3,7 @@
 // element-wise helpers) into the reference's operations.  Every composition cites the reference lines
 // it reproduces; scratch use follows the reference's M / M' / M'' roles where that matters for the
 // documented aliasing rules.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -214,6 +215,12 @@ template <typename T> struct Ctx {
         else if (cl_pays && cs_reg == 0) algo = SLA_LDR_ALGO_CLUSTER;
         else algo = SLA_LDR_ALGO_STREAMING;
         a.info = w.info;
+#ifdef SLA_LDR_INTERVALS   // diagnostics: time from "ldr! enqueued behind its input GEMM" to "ldr! finished" on the main stream
+        static cudaEvent_t evs[2][256]; static int nev = 0; static bool made = false;
+        if (!made) { for (int i = 0; i < 256; ++i) { cudaEventCreate(&evs[0][i]); cudaEventCreate(&evs[1][i]); } made = true; }
+        const int ei = nev % 256;
+        cudaEventRecord(evs[0][ei], s);
+#endif
         switch (algo) {
             case SLA_LDR_ALGO_PANEL: CK(ldr_pp_batched<T>(a, s)); break;
             case SLA_LDR_ALGO_MULTICTA: CK(ldr_mc_batched<T>(a, cs_mc, s)); break;
@@ -223,6 +230,15 @@ template <typename T> struct Ctx {
             case SLA_LDR_ALGO_CLUSTER: CK(ldr_cluster_batched<T>(a, s)); break;
             default: CK(ldr_batched<T>(a, s)); break;
         }
+#ifdef SLA_LDR_INTERVALS
+        cudaEventRecord(evs[1][ei], s);
+        if (++nev % 200 == 0) {
+            cudaStreamSynchronize(s);
+            float tot = 0.f, mx = 0.f;
+            for (int i = 0; i < 200; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, evs[0][i], evs[1][i]); tot += ms; mx = ms > mx ? ms : mx; }
+            fprintf(stderr, "[sla] ldr! intervals on the main stream: mean %.3f ms, max %.3f ms over 200 calls\n", tot / 200, mx);
+        }
+#endif
         h->last_ldr_algo = algo;
         ++h->ldr_algo_launches[algo];
         return 0;
