@@ -691,6 +691,45 @@ def test_chain_C4_size_short(S):
     check_chain(S, cfg, [0], "IpA")
 
 
+@pytest.mark.gpu
+def test_two_devices_in_one_process(S):
+    """ADVICE (round 1): kernel attributes (dynamic shared memory above 48 KB) and dispatch caches are per DEVICE, and a
+    handle is bound to its device.  One process drives two GPUs: GEMM, hybrid ldr! + tensor-core Q, LU inverse and a small
+    chain on cuda:1 after cuda:0 must give the same answers.  Skipped on a single-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    rng = np.random.default_rng(7)
+    n, batch = 256, 36
+    A, B = rand_matrix(rng, n, False, batch), rand_matrix(rng, n, False, batch)
+    Gr = A * (10.0 ** np.linspace(20, -20, n))[None, None, :]
+    res = []
+    for dev in (0, 1, 0):
+        with torch.cuda.device(dev):
+            d = f"cuda:{dev}"
+            dA, dB = S.to_device(A, d), S.to_device(B, d)
+            C = torch.zeros_like(dB)
+            S.gemm(C, dA, dB)
+            assert relerr(S.to_host(C), A @ B) < 1e-13
+            dG = S.to_device(Gr, d)
+            ws = S.ldr_workspace(dG)
+            F = S.ldr(dG, ws)
+            S.check_info(ws)
+            assert S.last_ldr_algo() == "hybrid"
+            rec = np.einsum("bij,bj,bjk->bik", S.to_host(F.L), F.d.cpu().numpy(), S.to_host(F.R))
+            assert relerr(rec, Gr) < 1e-12
+            X = dA.clone()
+            ld_, sg_ = S.inv_lu_(X, ws)
+            assert relerr(S.to_host(X), np.linalg.inv(A)) < 1e-9
+            cfg = S.synthetic.CONFIGS["C1"]
+            _, _, Gc, ldc, _ = run_chain(S, cfg, [0, 1], "IpA")     # the fused driver (graph, side streams) on this device
+            res.append((S.to_host(C), S.to_host(F.L), S.to_host(X), ld_.cpu().numpy(), Gc, ldc))
+            torch.cuda.synchronize()
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)      # same kernels, same inputs: bit-identical across devices
+    for a, b in zip(res[0], res[2]):
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("complex_", [False, True])
 def test_walker_sums(S, complex_):
     rng = np.random.default_rng(3)
