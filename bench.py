@@ -243,28 +243,45 @@ def ncu_record(kernel, cfg_name):
 
 
 def measure_gemm_kernel(torch, sla, cfg, reps=20):
-    """Average duration of the dominant kernel -- the batched DMMA GEMM that builds the group products
-    (shared expK x per-chain matrix, row-scaled epilogue) -- at the shape/batch the step launches it
-    with, timed with CUDA events on the launching stream."""
+    """Throughput of the dominant kernel -- the batched DMMA GEMM that builds the group products (shared expK x
+    per-chain matrix, row-scaled epilogue) -- in the pattern the step issues it: sla_greens_chain builds the group
+    products one group per launch (batch = chains), round-robin over TWO low-priority side streams, so two launches are
+    in flight together.  Timed with CUDA events on a parent stream that forks into / joins the two launching streams;
+    returns (ms per concurrent pair, FLOPs per pair, matrices per pair, TFLOP/s of ONE launch running alone)."""
     n = cfg.N
-    batch = cfg.chains * 2          # the fused driver builds the group products in sub-chunks of 2 groups
+    batch = cfg.chains
     dt = torch.complex128 if cfg.dtype.kind == "c" else torch.float64
     A = sla.to_device(cfg.expK())
-    B = torch.randn(batch, n, n, dtype=torch.float64, device="cuda").to(dt)
-    C = torch.empty_like(B)
-    for _ in range(2):
-        sla.gemm(C, A, B)
+    main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    bufs = []
+    for st in streams:
+        B = torch.randn(batch, n, n, dtype=torch.float64, device="cuda").to(dt)
+        bufs.append([B, torch.empty_like(B)])
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        sla.gemm(C, A, B)
-        B, C = C, B
-    e1.record()
-    e1.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    flops = (8.0 if cfg.dtype.kind == "c" else 2.0) * n ** 3 * batch
-    return ms, flops, batch
+    flops1 = (8.0 if cfg.dtype.kind == "c" else 2.0) * n ** 3 * batch
+
+    def run(nstreams, count):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event() for _ in range(nstreams)]
+        e0.record(main)
+        for i in range(nstreams):
+            streams[i].wait_event(e0)
+            with torch.cuda.stream(streams[i]):
+                for _ in range(count):
+                    sla.gemm(bufs[i][1], A, bufs[i][0])
+                    bufs[i].reverse()
+                ends[i].record(streams[i])
+        for ev in ends:
+            main.wait_event(ev)
+        e1.record(main)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / count
+
+    run(2, 2); run(1, 2)                      # warm-up (also creates the per-stream library handles)
+    ms_pair = run(2, reps)
+    ms_single = run(1, reps)
+    return ms_pair, 2 * flops1, 2 * batch, flops1 / (ms_single * 1e-3) / 1e12
 
 
 def measure_ldr_kernel(torch, sla, cfg, F, reps=10):
@@ -432,12 +449,16 @@ def run_gpu(args):
 
     roof = roof_ldr = cpub = None
     if rank == 0:
-        gm_ms, gm_flops, gm_batch = measure_gemm_kernel(torch, sla, cfg)
+        gm_ms, gm_flops, gm_batch, gm_single = measure_gemm_kernel(torch, sla, cfg)
         peak = measure_dgemm_peak(torch)
         achieved = gm_flops / (gm_ms * 1e-3) / 1e12
         step_tflops = cfg.flops_per_eval() * chains / (ms_total / steps * 1e-3) / 1e12
         rec = ncu_record("gemm_kernel", cfg.name)
         roof = {"bound": "tensor", "kernel": "sla::gemm_kernel (batched FP64 DMMA GEMM, group-product shape)",
+                "pattern": f"as sla_greens_chain issues it: one group per launch (batch {gm_batch // 2}), two launches in flight "
+                           f"on two side streams; launch_ms / launch_batch / flops_per_launch describe one concurrent PAIR; "
+                           f"a single launch of batch {gm_batch // 2} running alone: {gm_single:.2f} TFLOP/s",
+                "single_launch_alone_tflops": gm_single,
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": rec["dram_bytes_per_launch"] if rec else None,
                 "traffic_source": (f"{rec['source']} @ {rec['commit']} (ncu dram read+write per launch)" if rec else None),
