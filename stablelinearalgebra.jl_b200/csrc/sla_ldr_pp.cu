@@ -19,6 +19,7 @@
 // One CTA per matrix; the matrix lives in global memory (L2), the panel in shared memory.  No per-column pass over the
 // trailing matrix, no per-column cluster exchange: per column only CTA-local barriers and 2 NB-column-wide operations.
 #include <cstdio>
+#include <cstdlib>
 
 #include "sla_cta.cuh"
 #include "sla_kernels.h"
@@ -528,10 +529,17 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) ldr_pp_kernel(LdrArgs<T> p, in
     PP_DUMP();
 }
 
+// Panel width: as wide as the shared memory allows, at most 32; real matrices of n <= 256 take 16 (measured faster: C2 step
+// 31.8 ms against 33.1 with NB = 32 and 35.2 with NB = 8; N = 400: 16 and 32 equal).  The width does NOT decide the accuracy:
+// on the C1-size sweep the G(0) error of this mode is 5e-12 .. 3e-9 for NB = 8, 16 and 32 alike (strict path: 6e-13 .. 3e-11;
+// profiles/ldr_panel_r2.txt).  SLA_PP_NB=8|16|32 overrides (experiments).
 template <typename T> int pp_pick_nb(int n) {
     const size_t limit = 227 * 1024;
-    if (pp_smem_bytes<T>(n, 32) <= limit) return 32;
-    if (pp_smem_bytes<T>(n, 16) <= limit) return 16;
+    static const int forced = getenv("SLA_PP_NB") ? atoi(getenv("SLA_PP_NB")) : 0;
+    int cap = (!is_cplx<T>::value && n <= 256) ? 16 : 32;
+    if (forced == 8 || forced == 16 || forced == 32) cap = forced;
+    if (cap >= 32 && pp_smem_bytes<T>(n, 32) <= limit) return 32;
+    if (cap >= 16 && pp_smem_bytes<T>(n, 16) <= limit) return 16;
     if (pp_smem_bytes<T>(n, 8) <= limit) return 8;
     return 0;
 }
