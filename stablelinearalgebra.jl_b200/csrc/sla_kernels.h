@@ -66,6 +66,7 @@ template <typename T> struct LuArgs {
     int* info;                               // optional per-matrix: 0 ok, k>0 = U(k,k) exactly zero
     int invert, copy_back;
     int n; int batch;
+    int pipe;                                // set by lu_batched: clusters overlap the forward sweep with the factorisation
 };
 template <typename T> cudaError_t lu_batched(const LuArgs<T>& p, cudaStream_t s);
 template <typename T> bool lu_supported(int n);   // the panels of an n x n matrix fit the shared memory of one CTA

@@ -45,7 +45,11 @@ template <typename T> __host__ __device__ inline size_t lu_smem_bytes(int n, int
 #define LUP_DUMP(tag) do { } while (0)
 #endif
 
-template <typename T, int NB>
+// PIPE: the CTA runs as rank 0 of a cluster whose other CTAs form L^-1 P (the forward sweep of the inverse) panel by
+// panel WHILE this CTA factorises: one cluster barrier per panel, right after the panel (final with respect to its own
+// pivots) and its pivots are published.  The later interchanges that touch this panel's rows in global memory only
+// happen after the NEXT barrier, i.e. after the peers have consumed the panel (lu_forward_pipe).
+template <typename T, int NB, bool PIPE = false>
 __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int ld, int* ipiv, int* rowpos,
                           int* tl, int* tsrc, double* redv, int* redi, int* misc, int* info_out) {
     const int tid = threadIdx.x;
@@ -195,6 +199,10 @@ __device__ void lu_factor(T* __restrict__ A, int lda, int n, T* Ps, T* Us, int l
         // ---- panel back to global
         for (int i = 0; i < jb; ++i)
             for (int r = p0 + tid; r < n; r += CTA_THREADS) A[(long long)(p0 + i) * lda + r] = Ps[(size_t)i * ld + r];
+        if constexpr (PIPE) {
+            __threadfence();
+            cg::this_cluster().sync();   // panel p0 and ipiv[p0, kend) are published
+        }
         LUP(1);
         // ---- net row permutation of this panel (thread 0 simulates the jb interchanges)
         if (tid == 0) {
@@ -298,55 +306,96 @@ __device__ void lu_logdet(const T* __restrict__ A, int lda, int n, const int* ip
     __syncthreads();
 }
 
+// One panel of the forward sweep Y = L^-1 (.) on the columns [c_lo, c_hi) of X: substitution with the unit-lower L11 in
+// registers (thread per column), then the rank-NB update of the rows below on the tensor cores.
+template <typename T, int NB>
+__device__ void lu_forward_step(const T* __restrict__ A, int lda, int n, T* __restrict__ X, int ldx, T* Ps, T* Us, int ld,
+                                int p0, int c_lo, int c_hi) {
+    const int tid = threadIdx.x;
+    const int jb = min(NB, n - p0), kend = p0 + jb;
+    for (int i = 0; i < NB; ++i)
+        for (int r = tid; r < n; r += CTA_THREADS)
+            Ps[(size_t)i * ld + r] = (i < jb && r > p0 + i) ? A[(long long)(p0 + i) * lda + r] : mk<T>(0.0);
+    __syncthreads();
+    for (int c = c_lo + tid; c < c_hi; c += CTA_THREADS) {
+        T a[NB];
+        T* col = X + (long long)c * ldx + p0;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) a[i] = (i < jb) ? col[i] : mk<T>(0.0);
+#pragma unroll
+        for (int i = 1; i < NB; ++i) {
+            if (i < jb) {
+#pragma unroll
+                for (int q = 0; q < i; ++q) fms(a[i], Ps[(size_t)q * ld + p0 + i], a[q]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            if (i < jb) col[i] = a[i];
+            Us[(size_t)i * ld + c] = a[i];
+        }
+    }
+    __syncthreads();
+    cta_rank_update<T, false>(X, ldx, kend, n, c_lo, c_hi, Ps, Us, ld, jb, n - 1);
+    __syncthreads();
+}
+
+// Rank >= 1 of a PIPE cluster: Y = L^-1 P I (or L^-1 P RHS) on the columns [c_lo, c_hi) of X, one panel per cluster
+// barrier, concurrently with the factorisation in rank 0 (lu_factor<PIPE>).  P is applied incrementally -- the
+// interchanges of panel p to the rows of X when panel p arrives -- which is equivalent to permuting first: the rows of L
+// below a panel and the rows of X are then in the same (time-p) order, and later interchanges permute both alike.
+template <typename T, int NB>
+__device__ void lu_forward_pipe(const T* __restrict__ A, int lda, int n, T* __restrict__ X, int ldx, T* Ps, T* Us, int ld,
+                                const int* __restrict__ ipiv0, int* piv_s, const T* __restrict__ rhs, int ldrhs,
+                                int c_lo, int c_hi) {
+    const int tid = threadIdx.x;
+    for (int c = c_lo + (tid >> 5); c < c_hi; c += CTA_WARPS)
+        for (int r = (tid & 31); r < n; r += 32)
+            X[(long long)c * ldx + r] = rhs ? rhs[(long long)c * ldrhs + r] : mk<T>(r == c ? 1.0 : 0.0);
+    __syncthreads();
+    for (int p0 = 0; p0 < n; p0 += NB) {
+        const int jb = min(NB, n - p0);
+        cg::this_cluster().sync();       // rank 0 has published panel p0 and its pivots
+        if (tid < jb) piv_s[tid] = ipiv0[p0 + tid];   // distributed shared memory of rank 0
+        __syncthreads();
+        // the panel's interchanges, in order, on this CTA's columns: a thread per column
+        for (int c = c_lo + tid; c < c_hi; c += CTA_THREADS) {
+            T* col = X + (long long)c * ldx;
+            for (int j = 0; j < jb; ++j) {
+                const int k = p0 + j, pv = piv_s[j];
+                if (pv != k) { const T t = col[k]; col[k] = col[pv]; col[pv] = t; }
+            }
+        }
+        __syncthreads();
+        lu_forward_step<T, NB>(A, lda, n, X, ldx, Ps, Us, ld, p0, c_lo, c_hi);
+    }
+}
+
 // X = A^-1 * RHS from the LU factors (RHS = identity when rhs == nullptr, i.e. the inverse), columns [c_lo, c_hi) of X
 // only: the columns of X are independent, so the CTAs of a cluster split them (see lu_kernel).
 template <typename T, int NB>
 __device__ void lu_inverse(const T* __restrict__ A, int lda, int n, T* __restrict__ X, int ldx, T* Ps, T* Us,
                            int ld, const int* ipiv, int* rowpos, const T* __restrict__ rhs, int ldrhs, T* rdiag,
-                           int c_lo, int c_hi) {
+                           int c_lo, int c_hi, bool skip_forward = false) {
     const int tid = threadIdx.x;
-    // X = P (row-permuted identity): row r of P*I is e_{src(r)}
-    for (int r = tid; r < n; r += CTA_THREADS) rowpos[r] = r;
-    __syncthreads();
-    if (tid == 0)
-        for (int k = 0; k < n; ++k) {
-            int pk = ipiv[k];
-            if (pk != k) { int t = rowpos[k]; rowpos[k] = rowpos[pk]; rowpos[pk] = t; }
-        }
-    __syncthreads();
-    for (int c = c_lo + (tid >> 5); c < c_hi; c += CTA_WARPS)
-        for (int r = (tid & 31); r < n; r += 32)
-            X[(long long)c * ldx + r] = rhs ? rhs[(long long)c * ldrhs + rowpos[r]] : mk<T>(rowpos[r] == c ? 1.0 : 0.0);
-    __syncthreads();
-    // ---- forward sweep: Y = L^-1 P
-    for (int p0 = 0; p0 < n; p0 += NB) {
-        const int jb = min(NB, n - p0), kend = p0 + jb;
-        for (int i = 0; i < NB; ++i)
-            for (int r = tid; r < n; r += CTA_THREADS)
-                Ps[(size_t)i * ld + r] = (i < jb && r > p0 + i) ? A[(long long)(p0 + i) * lda + r] : mk<T>(0.0);
+    if (!skip_forward) {
+        // X = P (row-permuted identity): row r of P*I is e_{src(r)}
+        for (int r = tid; r < n; r += CTA_THREADS) rowpos[r] = r;
         __syncthreads();
-        for (int c = c_lo + tid; c < c_hi; c += CTA_THREADS) {
-            T a[NB];
-            T* col = X + (long long)c * ldx + p0;
-#pragma unroll
-            for (int i = 0; i < NB; ++i) a[i] = (i < jb) ? col[i] : mk<T>(0.0);
-#pragma unroll
-            for (int i = 1; i < NB; ++i) {
-                if (i < jb) {
-#pragma unroll
-                    for (int q = 0; q < i; ++q) fms(a[i], Ps[(size_t)q * ld + p0 + i], a[q]);
-                }
+        if (tid == 0)
+            for (int k = 0; k < n; ++k) {
+                int pk = ipiv[k];
+                if (pk != k) { int t = rowpos[k]; rowpos[k] = rowpos[pk]; rowpos[pk] = t; }
             }
-#pragma unroll
-            for (int i = 0; i < NB; ++i) {
-                if (i < jb) col[i] = a[i];
-                Us[(size_t)i * ld + c] = a[i];
-            }
-        }
         __syncthreads();
-        cta_rank_update<T, false>(X, ldx, kend, n, c_lo, c_hi, Ps, Us, ld, jb, n - 1);
+        for (int c = c_lo + (tid >> 5); c < c_hi; c += CTA_WARPS)
+            for (int r = (tid & 31); r < n; r += 32)
+                X[(long long)c * ldx + r] = rhs ? rhs[(long long)c * ldrhs + rowpos[r]] : mk<T>(rowpos[r] == c ? 1.0 : 0.0);
         __syncthreads();
     }
+    // ---- forward sweep: Y = L^-1 P   (skipped when the cluster peers formed it during the factorisation)
+    if (!skip_forward)
+        for (int p0 = 0; p0 < n; p0 += NB) lu_forward_step<T, NB>(A, lda, n, X, ldx, Ps, Us, ld, p0, c_lo, c_hi);
     // ---- backward sweep: X = U^-1 Y
     const int npan = (n + NB - 1) / NB;
     for (int pi = npan - 1; pi >= 0; --pi) {
@@ -410,11 +459,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) lu_kernel(LuArgs<T> p) {
     // three LU factorisations and the FIRST failure has to survive (the reference throws at every getrf!, lu.jl:75)
     int* info = p.info ? p.info + b : nullptr;
     double logdet = 0.0; T sgn = mk<T>(1.0);
+    // PIPE (a cluster forming an inverse / a solve): rank 0 factorises, the other ranks form Y = L^-1 P panel by panel at
+    // the same time (lu_forward_pipe), their columns of X split evenly among them; afterwards only the backward sweep is
+    // left, split over ALL ranks.  SLA_LU_PIPE=0 (p.pipe == 0): the factorisation first, then both sweeps split.
+    const bool pipe = (CS > 1) && p.invert && p.pipe;
+    T* Xm = p.X ? p.X + (long long)b * p.strideX : nullptr;
+    T* rhs_m = p.rhs ? p.rhs + (long long)b * p.strideRhs : nullptr;
     if (rank == 0) {
-        lu_factor<T, NB>(A, p.lda, n, Ps, Us, ld, ipiv, rowpos, tl, tsrc, redv, redi, misc, info);
+        if (pipe) lu_factor<T, NB, true>(A, p.lda, n, Ps, Us, ld, ipiv, rowpos, tl, tsrc, redv, redi, misc, info);
+        else lu_factor<T, NB, false>(A, p.lda, n, Ps, Us, ld, ipiv, rowpos, tl, tsrc, redv, redi, misc, info);
         lu_logdet<T>(A, p.lda, n, ipiv, redv, redt, logdet, sgn);
         if (p.ipiv_out)
             for (int i = tid; i < n; i += CTA_THREADS) p.ipiv_out[(long long)b * n + i] = ipiv[i] + 1;
+    } else if (pipe) {
+        const int fper = (((n + CS - 2) / (CS - 1)) + 31) & ~31;
+        const int f_lo = min(n, (rank - 1) * fper), f_hi = min(n, f_lo + fper);
+        lu_forward_pipe<T, NB>(A, p.lda, n, Xm, p.ldx, Ps, Us, ld, cl.map_shared_rank(ipiv, 0), tl, rhs_m, p.ldrhs, f_lo, f_hi);
     }
     if (CS > 1) {
         __threadfence();   // the factors in global memory are read by the peers after the barrier
@@ -429,9 +489,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) lu_kernel(LuArgs<T> p) {
         // column slice of this CTA (multiples of the 32-column warp tile of cta_rank_update)
         const int per = (((n + CS - 1) / CS) + 31) & ~31;
         const int c_lo = min(n, rank * per), c_hi = min(n, c_lo + per);
-        T* X = p.X + (long long)b * p.strideX;
-        T* rhs = p.rhs ? p.rhs + (long long)b * p.strideRhs : nullptr;
-        lu_inverse<T, NB>(A, p.lda, n, X, p.ldx, Ps, Us, ld, ipiv, rowpos, rhs, p.ldrhs, redt, c_lo, c_hi);
+        T* X = Xm;
+        T* rhs = rhs_m;
+        lu_inverse<T, NB>(A, p.lda, n, X, p.ldx, Ps, Us, ld, ipiv, rowpos, rhs, p.ldrhs, redt, c_lo, c_hi, pipe);
         if (rhs) {   // ldiv_lu!: the solution replaces the right-hand side (src/lu.jl:167-176)
             __syncthreads();
             for (int c = c_lo + (tid >> 5); c < c_hi; c += CTA_WARPS)
@@ -469,8 +529,11 @@ static int lu_cluster_size(int n, int batch, int invert) {
     return 1;
 }
 
-template <typename T> cudaError_t lu_batched(const LuArgs<T>& p, cudaStream_t stream) {
-    if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
+template <typename T> cudaError_t lu_batched(const LuArgs<T>& p_in, cudaStream_t stream) {
+    if (p_in.batch <= 0 || p_in.n <= 0) return cudaSuccess;
+    static const bool pipe_off = getenv("SLA_LU_PIPE") && atoi(getenv("SLA_LU_PIPE")) == 0;   // A/B experiments
+    LuArgs<T> p = p_in;
+    p.pipe = pipe_off ? 0 : 1;
     int nb = (sizeof(T) == 8) ? LU_NB : LU_NB / 2;  // register-resident substitution columns: a[NB]
     const size_t limit = 227 * 1024;
     while (nb >= 8 && lu_smem_bytes<T>(p.n, nb) > limit) nb >>= 1;
