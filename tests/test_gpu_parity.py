@@ -216,6 +216,38 @@ def test_det_inv_lu(S, n, complex_):
         assert relerr(Xi[b], np.linalg.inv(A[b])) < 1e-13 * np.linalg.cond(A[b]) + 1e-12
 
 
+@pytest.mark.parametrize("n,batch,complex_", [(256, 64, False), (200, 5, False), (130, 70, True), (512, 6, False), (1024, 2, False)])
+def test_inv_lu_cluster_pipeline(S, n, batch, complex_):
+    """The cluster form of the LU inverse (2 or 4 CTAs per matrix when the batch leaves SMs free): the peers form L^-1 P
+    panel by panel WHILE rank 0 factorises (csrc/sla_lu.cu lu_forward_pipe).  Same answers as numpy at every cluster size,
+    the ldiv_lu! (right-hand side) form as well, and bit-identical from run to run (a race between the factorising CTA
+    and its peers would show up as run-to-run differences)."""
+    rng = np.random.default_rng(17 * n + batch)
+    A = rand_matrix(rng, n, complex_, batch)
+    dA = S.to_device(A)
+    ws = S.ldr_workspace(dA)
+    outs = []
+    for _ in range(4):
+        X = dA.clone()
+        logdet, sgn = S.inv_lu_(X, ws)
+        S.check_info(ws)
+        outs.append((S.to_host(X), logdet.cpu().numpy().copy(), sgn.cpu().numpy().copy()))
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) and np.array_equal(o[2], outs[0][2])
+    Xi = outs[0][0]
+    for b in sorted({0, batch // 2, batch - 1}):
+        cond = np.linalg.cond(A[b])
+        assert relerr(Xi[b], np.linalg.inv(A[b])) < 1e-13 * cond + 1e-12
+        sref, lref = np.linalg.slogdet(A[b])
+        assert abs(outs[0][1][b] + lref) < 1e-10 * max(1, n) and abs(outs[0][2][b] - np.conj(sref)) < 1e-10
+    Bm = rand_matrix(rng, n, complex_, batch)
+    dB = S.to_device(Bm)
+    S.ldiv_lu_(dA.clone(), dB, ws)
+    Bs = S.to_host(dB)
+    for b in (0, batch - 1):
+        assert relerr(Bs[b], np.linalg.solve(A[b], Bm[b])) < 1e-13 * np.linalg.cond(A[b]) + 1e-12
+
+
 def test_lu_singular_info(S):
     A = np.zeros((2, 8, 8))
     A[0] = np.eye(8)
