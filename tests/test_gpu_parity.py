@@ -702,6 +702,26 @@ def test_chain_small_complex_IpUV(S):
     check_chain(S, cfg, [5, 9], "IpA")
 
 
+@pytest.mark.parametrize("ng", [1, 2, 3, 5])
+def test_chain_few_groups(S, ng):
+    """Edge cases of the fused driver's schedule: one to five stabilisation groups (a single side stream for <= 2
+    sub-chunks, round-robin over two beyond that), the first stabilisation of F -- and of U in inv_IpUV!, whose state takes
+    over at group ng / 2 -- reading B_bar directly instead of multiplying the identity; real and complex, an n_stab of 1."""
+    syn = S.synthetic
+    cfg = syn.HubbardConfig("few", 4, 5 * ng, 5, 3)
+    check_chain(S, cfg, [0, 1, 2], "IpA")
+    cfgc = syn.HubbardConfig("fewc", 4, 4 * ng, 4, 2, dtype=np.complex128, phase=0.3, inverse="IpUV")
+    if ng >= 2:                                                # inv_IpUV! needs a V and a U half: at least two groups
+        check_chain(S, cfg, [0, 1, 2], "IpUV")
+        check_chain(S, cfgc, [0, 3], "IpUV")
+    else:
+        with pytest.raises(S.SlaError):
+            run_chain(S, cfg, [0], "IpUV")
+        check_chain(S, cfgc, [0, 3], "IpA")
+    cfg1 = syn.HubbardConfig("few1", 4, ng, 1, 2)              # n_stab = 1: no group-product GEMMs at all
+    check_chain(S, cfg1, [1, 2], "IpA")
+
+
 def test_chain_C2_sample(S):
     cfg = S.synthetic.CONFIGS["C2"]           # N=256, L=200 (a sample of the 64 chains vs the oracle)
     check_chain(S, cfg, [0, 1, 63], "IpA")
