@@ -56,6 +56,7 @@ extern "C" {
 #define SLA_LDR_ALGO_BLOCKED 5   /* blocked panel + tensor-core trailing update (csrc/sla_ldr_blk.cu) */
 #define SLA_LDR_ALGO_MULTICTA 6  /* L2-streaming, a cluster of 2-8 CTAs per matrix (csrc/sla_ldr_mc.cu) */
 #define SLA_LDR_ALGO_PANEL 7     /* panel-restricted pivoting, opt-in mode SLA_LDR_PIVOT=panel (csrc/sla_ldr_pp.cu) */
+#define SLA_LDR_ALGO_SMALL 8     /* n <= 64: one CTA per matrix, matrix in registers (csrc/sla_ldr_small.cu) */
 /* per-matrix info codes (sla_workspace_info): k > 0 = U(k,k) exactly zero or not finite in an LU (src/lu.jl:75,91);
  * SLA_INFO_RANGE = a column norm of an ldr! input left the range in which squared norms are representable */
 #define SLA_INFO_RANGE (-1)

@@ -17,7 +17,7 @@ SLA_OP_N, SLA_OP_C = 0, 1
 SLA_INV_IPA, SLA_INV_IPUV = 0, 1
 SLA_ENOTIMPL, SLA_EDEVICE = -100, -101
 SLA_INFO_RANGE = -1
-LDR_ALGOS = {0: "none", 1: "reg", 2: "cluster", 3: "streaming", 4: "hybrid", 5: "blocked", 6: "multicta", 7: "panel"}
+LDR_ALGOS = {0: "none", 1: "reg", 2: "cluster", 3: "streaming", 4: "hybrid", 5: "blocked", 6: "multicta", 7: "panel", 8: "small"}
 
 _vp, _i, _ll, _sz, _dbl = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_double
 _common = [_vp, _i, _i, _i]  # handle, dtype, n, batch

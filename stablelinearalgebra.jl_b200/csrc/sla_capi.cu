@@ -14,13 +14,14 @@
 
 using namespace sla;
 
+constexpr int SLA_N_LDR_ALGOS = 16;          // size of the per-algorithm counters (SLA_LDR_ALGO_* < 16)
 static long long* g_ldr_prof = nullptr;   // diagnostics only (sla_debug_set_ldr_prof)
 
 struct sla_handle_s {
     cudaStream_t stream;
     int device = 0;           // the device the handle was created on (sla_create); every call checks it is current
     int last_ldr_algo = 0;    // SLA_LDR_ALGO_* of the most recent LDR factorisation launched through this handle
-    unsigned long long ldr_algo_launches[8] = {};   // factorisations launched per algorithm
+    unsigned long long ldr_algo_launches[SLA_N_LDR_ALGOS] = {};   // factorisations launched per algorithm
     // fused driver only: a lower-priority side stream on which the group products (independent of the chain
     // state) are built while the chain's latency-bound LDR kernels leave SMs idle; created lazily
     cudaStream_t side = nullptr;
@@ -36,7 +37,7 @@ struct sla_handle_s {
         unsigned long long key[20] = {};
         cudaGraphExec_t exec = nullptr;
         unsigned long long kernels = 0;            // kernel launches inside the graph (sla_launch_count)
-        unsigned long long algo_launches[8] = {};  // LDR factorisations per algorithm inside the graph
+        unsigned long long algo_launches[SLA_N_LDR_ALGOS] = {};  // LDR factorisations per algorithm inside the graph
         int last_algo = 0;
     } graphs[4];
     int graph_next = 0;
@@ -156,7 +157,7 @@ template <typename T> struct Ctx {
             const char* e = getenv("SLA_LDR_ALGO");
             if (getenv("SLA_LDR_STREAMING")) return 3;
             if (!e) return 0;
-            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : (e[0] == 'h' ? 4 : (e[0] == 'b' ? 5 : (e[0] == 'm' ? 6 : (e[0] == 'p' ? 7 : 0))))));
+            return e[0] == 'r' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 's' ? 3 : (e[0] == 'h' ? 4 : (e[0] == 'b' ? 5 : (e[0] == 'm' ? 6 : (e[0] == 'p' ? 7 : (e[0] == 't' ? 8 : 0)))))));
         }();
         // SLA_LDR_PIVOT=panel: panel-restricted pivoting (sla_ldr_pp.cu) for every factorisation -- a different pivot
         // sequence than ?geqp3, hence a mode, never chosen by the dispatcher on its own
@@ -200,6 +201,10 @@ template <typename T> struct Ctx {
             else if (batch <= 66) cs_mc = 2;
             if (forced == 6) cs_mc = (mc_forced_cs == 2 || mc_forced_cs == 4 || mc_forced_cs == 8) ? mc_forced_cs : 4;
         }
+        // n <= 64: one CTA per matrix with the matrix in registers and one barrier per column (sla_ldr_small.cu) -- the
+        // cluster kernels' per-column machinery costs ~3000 cycles per column at this size, the small kernel's chain is a
+        // few hundred; SLA_LDR_SMALL=0 switches it off, SLA_LDR_ALGO=tiny forces it
+        static const bool small_on = !(getenv("SLA_LDR_SMALL") && atoi(getenv("SLA_LDR_SMALL")) == 0);
         int algo;
         if (forced == 7 || (forced == 0 && panel_mode)) { if (!ldr_pp_supported<T>(n)) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_PANEL; }
         else if (forced == 6) { if (cs_mc == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_MULTICTA; }
@@ -210,6 +215,8 @@ template <typename T> struct Ctx {
         else if (forced == 1) { if (cs_reg == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_REG; }
         else if (forced == 2) { if (cs_cl == 0) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_CLUSTER; }
         else if (forced == 3) algo = SLA_LDR_ALGO_STREAMING;
+        else if (forced == 8) { if (!ldr_small_supported<T>(n)) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_SMALL; }
+        else if (small_on && ldr_small_supported<T>(n)) algo = SLA_LDR_ALGO_SMALL;
         else if (hyb_pays) algo = SLA_LDR_ALGO_HYBRID;
         else if (reg_pays) algo = SLA_LDR_ALGO_REG;
         else if (cl_pays && cs_reg == 0) algo = SLA_LDR_ALGO_CLUSTER;
@@ -228,6 +235,7 @@ template <typename T> struct Ctx {
             case SLA_LDR_ALGO_HYBRID: CK(ldr_hyb_batched<T>(a, s)); break;
             case SLA_LDR_ALGO_REG: CK(ldr_reg_batched<T>(a, s)); break;
             case SLA_LDR_ALGO_CLUSTER: CK(ldr_cluster_batched<T>(a, s)); break;
+            case SLA_LDR_ALGO_SMALL: CK(ldr_small_batched<T>(a, s)); break;
             default: CK(ldr_batched<T>(a, s)); break;
         }
 #ifdef SLA_LDR_INTERVALS
@@ -979,7 +987,7 @@ int sla_destroy(sla_handle_t handle) {
 int sla_last_ldr_algo(sla_handle_t handle) { return handle ? handle->last_ldr_algo : -1; }
 
 unsigned long long sla_ldr_algo_launches(sla_handle_t handle, int algo) {
-    return (handle && algo >= 0 && algo < 8) ? handle->ldr_algo_launches[algo] : 0ull;
+    return (handle && algo >= 0 && algo < SLA_N_LDR_ALGOS) ? handle->ldr_algo_launches[algo] : 0ull;
 }
 
 int sla_set_stream(sla_handle_t handle, void* stream) {
@@ -1350,8 +1358,8 @@ int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L, int n_s
         if (e.exec) { cudaGraphExecDestroy(e.exec); e.exec = nullptr; }
         e.used = false;
         const unsigned long long k0 = g_launch_count.load();
-        unsigned long long a0[8];
-        for (int i = 0; i < 8; ++i) a0[i] = h->ldr_algo_launches[i];
+        unsigned long long a0[SLA_N_LDR_ALGOS];
+        for (int i = 0; i < SLA_N_LDR_ALGOS; ++i) a0[i] = h->ldr_algo_launches[i];
         if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); h->graph_broken = true; return direct(); }
         const int rc = direct();
         cudaGraph_t graph = nullptr;
@@ -1359,7 +1367,7 @@ int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L, int n_s
         // the launches were recorded, not executed: take them out of the counters again (a replay adds them back)
         const unsigned long long kernels = g_launch_count.load() - k0;
         g_launch_count -= kernels;
-        for (int i = 0; i < 8; ++i) { e.algo_launches[i] = h->ldr_algo_launches[i] - a0[i]; h->ldr_algo_launches[i] = a0[i]; }
+        for (int i = 0; i < SLA_N_LDR_ALGOS; ++i) { e.algo_launches[i] = h->ldr_algo_launches[i] - a0[i]; h->ldr_algo_launches[i] = a0[i]; }
         if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
@@ -1378,7 +1386,7 @@ int sla_greens_chain(sla_handle_t h, int dtype, int n, int batch, int L, int n_s
     }
     CK(cudaGraphLaunch(g->exec, h->stream));
     g_launch_count += g->kernels;
-    for (int i = 0; i < 8; ++i) h->ldr_algo_launches[i] += g->algo_launches[i];
+    for (int i = 0; i < SLA_N_LDR_ALGOS; ++i) h->ldr_algo_launches[i] += g->algo_launches[i];
     h->last_ldr_algo = g->last_algo;
     return 0;
 }

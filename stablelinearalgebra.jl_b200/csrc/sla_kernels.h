@@ -53,6 +53,9 @@ template <typename T> bool ldr_mc_supported(int n);
 // panel-restricted pivoting (sla_ldr_pp.cu): NOT the ?geqp3 pivot sequence -- the opt-in mode SLA_LDR_PIVOT=panel
 template <typename T> cudaError_t ldr_pp_batched(const LdrArgs<T>& p, cudaStream_t s);
 template <typename T> bool ldr_pp_supported(int n);
+// small matrices (sla_ldr_small.cu; n <= 64): one CTA per matrix, matrix in registers, one barrier per column
+template <typename T> cudaError_t ldr_small_batched(const LdrArgs<T>& p, cudaStream_t s);
+template <typename T> bool ldr_small_supported(int n);
 // Q = H_0...H_{n-1} I on the FP64 tensor cores after a factorisation-only launch (real, n <= 256; taus in p.Twork)
 cudaError_t orgq_dmma_batched(const LdrArgs<double>& p, cudaStream_t s);
 

@@ -858,9 +858,38 @@ def test_ldr_hybrid_shape_edge_inputs(S):
             assert relerr((L[b] * d[b][None, :]) @ R[b], B[b]) < 1e-12
 
 
-@pytest.mark.parametrize("algo", ["streaming", "cluster", "hyb", "hyb+oneq", "hyb+qvec", "blk", "mc", "mc+cs2", "mc+cs8"])
+@pytest.mark.parametrize("complex_", [False, True])
+def test_ldr_small_kernel(S, complex_):
+    """n <= 64 is served by the one-CTA-per-matrix register kernel (csrc/sla_ldr_small.cu): every size class (n <= 32
+    and n <= 64 instantiations, n not a multiple of 4, n = 1), batches of one and of several hundred matrices,
+    column-graded input, exact ties (identity), L / d / R entry by entry against the LAPACK oracle on generic input,
+    and run-to-run bit identity."""
+    if os.environ.get("SLA_LDR_ALGO") or os.environ.get("SLA_LDR_PIVOT") or os.environ.get("SLA_LDR_SMALL"):
+        pytest.skip("another LDR kernel is forced in this process")
+    rng = np.random.default_rng(77)
+    for n, batch in [(1, 2), (2, 1), (3, 5), (7, 1), (31, 2), (32, 1), (33, 3), (50, 2), (63, 1), (64, 1), (64, 300), (20, 700)]:
+        A = rand_matrix(rng, n, complex_, batch)
+        F, ws = check_ldr(S, A)
+        assert S.last_ldr_algo() == "small"
+        L, d, R = S.to_host(F.L), F.d.cpu().numpy(), S.to_host(F.R)
+        for b in range(0, batch, max(1, batch // 3)):
+            Ab = np.asfortranarray(A[b])
+            Fo = O.ldr(Ab, O.ldr_workspace(Ab))
+            assert np.max(np.abs(L[b] - Fo.L)) < 1e-11 and np.max(np.abs(R[b] - Fo.R)) < 1e-11
+            assert np.max(np.abs(d[b] / Fo.d - 1)) < 1e-11
+        F2 = S.ldr(S.to_device(A), ws)
+        torch.cuda.synchronize()
+        assert torch.equal(F2.L, F.L) and torch.equal(F2.d, F.d) and torch.equal(F2.R, F.R)
+    check_ldr(S, graded_matrix(rng, 48, complex_, 80, 4))
+    check_ldr(S, graded_matrix(rng, 64, complex_, 120, 2))
+    F, _ = check_ldr(S, np.eye(13)[None] * (1.0 + 0j if complex_ else 1.0))
+    assert S.last_ldr_algo() == "small"
+    assert np.array_equal(S.to_host(F.L)[0], np.eye(13)) and np.array_equal(S.to_host(F.R)[0], np.eye(13))
+
+
+@pytest.mark.parametrize("algo", ["reg", "streaming", "cluster", "hyb", "hyb+oneq", "hyb+qvec", "blk", "mc", "mc+cs2", "mc+cs8"])
 def test_other_ldr_kernels_subprocess(algo):
-    """Default LDR kernel for n <= 256 is the register-resident cluster kernel.  The shared-memory cluster
+    """Default LDR kernel for n <= 64 is the small one-CTA kernel, for 64 < n <= 256 the register-resident cluster kernel.  The shared-memory cluster
     kernel (256 < n <= 512, e.g. C5's N=400) and the L2-streaming kernel (larger n, e.g. C4's N=1024) are
     forced through SLA_LDR_ALGO in a child process and must pass the same checks."""
     import os
@@ -883,7 +912,7 @@ def test_other_ldr_kernels_subprocess(algo):
                "or forced_algo_ran")
     if algo.startswith("mc"):       # any n; the sizes it is dispatched for by default (n > 512) included
         sel += " or ldr_n512_and_n1024"
-    env["SLA_EXPECT_ALGO"] = {"streaming": "streaming", "cluster": "cluster", "blk": "blocked", "mc": "multicta",
+    env["SLA_EXPECT_ALGO"] = {"reg": "reg", "streaming": "streaming", "cluster": "cluster", "blk": "blocked", "mc": "multicta",
                               "mc+cs2": "multicta", "mc+cs8": "multicta"}.get(algo, "hybrid")
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k", sel],
                        env=env, capture_output=True, text=True, timeout=900)
