@@ -1,0 +1,28 @@
+"""Cycles per phase of the small-matrix LDR kernel, version 2 (thread 0 of CTA 0; library built with -DSLA_SMALL_PROFILE and
+selected through SLA_B200_LIB): python profiles/ldr_small_phases.py [N] [batch]"""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sla_b200 as sla
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+rng = np.random.default_rng(0)
+A = rng.standard_normal((batch, n, n)) * 10.0 ** rng.uniform(-20, 20, size=(batch, 1, n))
+dA = sla.to_device(A)
+ws = sla.ldr_workspace(dA)
+F = sla.ldr(dA)
+prof = torch.zeros(128, dtype=torch.int64, device="cuda")
+lib = sla.load()
+for it in range(3):
+    sla.ldr_(F, dA, ws)
+torch.cuda.synchronize()
+lib.sla_debug_set_ldr_prof(prof.data_ptr())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); sla.ldr_(F, dA, ws); e1.record(); torch.cuda.synchronize()
+lib.sla_debug_set_ldr_prof(None)
+p = prof.cpu().numpy()[:8]
+names = ["norms+store", "barrier", "pivot (keys, 3 redux)", "pivot data + sqrt/rcp", "dot+shuffles+update", "(last barrier)",
+         "R extraction", "Q formation+store"]
+print(f"N={n} batch={batch} kernel={sla.last_ldr_algo()} {e0.elapsed_time(e1) * 1e3:.0f} us; cycles of thread 0, CTA 0: total {p.sum()}")
+for nm, v in zip(names, p):
+    print(f"  {nm:28s} {v:8d}  ({v / n:7.0f} per column)")

@@ -20,6 +20,8 @@
 // No physical column swaps: a column retired at step k keeps R'(0..k, k) in its registers and goes to its ORIGINAL
 // column of R = D^-1 R' P^T.  Q = H_0 ... H_{n-1} I needs no barrier at all: every thread applies the reflectors to its
 // slice of a column of the identity, reading them from the mirror.
+#include <stdlib.h>
+
 #include "sla_kernels.h"
 
 namespace sla {
@@ -259,9 +261,290 @@ __global__ void __launch_bounds__(NMAX * 4) ldr_small_kernel(LdrArgs<T> p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Version 2 (the default): the same algorithm with the ROW BLOCK of the current column as a compile-time constant.
+//
+// Version 1 above spends ~550 instructions per column and warp, most of them compares and selects: a thread's 16 rows
+// live in registers, so "rows above / on / below the diagonal" is decided per element and per column.  Here the column
+// loop is unrolled over KB = k / 4 (row = 4 i + q: the elements i < KB of every thread lie above row k, the elements
+// i > KB below it, and only element KB depends on the lane: q <, ==, > k % 4), so
+//   * dead rows cost nothing (the vector work of a column shrinks with k: half on average),
+//   * live rows are plain FMAs without predicates; one boundary element per thread carries the case distinction,
+//   * only the rows >= 4 KB of a column are mirrored / read back.
+// The reflector scalars are no longer computed speculatively by every column: once the pivot is known every thread
+// forms beta, tau and 1 / (alpha - beta) of THAT column from its published norm and its diagonal element, and the
+// square root and the reciprocals overlap with the raw dot product  s = sum_{r > k} conj(x_r) a_r, which does not
+// need them:  v^H a = a_k + conj(scal) s.  Loop body per column: publish norms and column -> barrier -> pivot -> apply.
+// The Q formation runs the same blocked form backwards (no barrier).
+// ---------------------------------------------------------------------------------------------
+// diagnostics (-DSLA_SMALL_PROFILE, profiles/ldr_small_phases.py): cycles per phase of the column loop, thread 0 of CTA 0
+struct SmallProf {
+#ifdef SLA_SMALL_PROFILE
+    long long t, acc[8];
+    __device__ __forceinline__ void start() { t = clock64(); for (int i = 0; i < 8; ++i) acc[i] = 0; }
+    __device__ __forceinline__ void stamp(int i) { const long long now = clock64(); acc[i] += now - t; t = now; }
+#else
+    __device__ __forceinline__ void start() {}
+    __device__ __forceinline__ void stamp(int) {}
+#endif
+};
+
+template <typename T, int RPL, int I0> __device__ __forceinline__ void load_rows(T (&x)[RPL], const T* __restrict__ src) {
+    if constexpr (is_cplx<T>::value) {
+#pragma unroll
+        for (int i = I0; i < RPL; ++i) x[i] = src[i];
+    } else {
+#pragma unroll
+        for (int i = (I0 & ~1); i < RPL; i += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(src + i);
+            x[i] = t.x; x[i + 1] = t.y;
+        }
+    }
+}
+template <typename T, int RPL, int I0> __device__ __forceinline__ void store_rows(T* __restrict__ dst, const T (&x)[RPL]) {
+    if constexpr (is_cplx<T>::value) {
+#pragma unroll
+        for (int i = I0; i < RPL; ++i) dst[i] = x[i];
+    } else {
+#pragma unroll
+        for (int i = (I0 & ~1); i < RPL; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(x[i], x[i + 1]);
+    }
+}
+
+// One reflector H = I - t v v^H, v = (1 in row k = 4 KB + kq, x * scal below), applied to the caller's slice `a` of a
+// column (t = conj(tau) during the factorisation, tau during the Q formation); x = the caller's rows of the reflector column.
+template <typename T, int RPL, int KB>
+__device__ __forceinline__ void apply_reflector(T (&a)[RPL], const T (&x)[RPL], int q, int kq, T t, T scal, bool update) {
+    T s0 = mk<T>(0.0), s1 = mk<T>(0.0);
+#pragma unroll
+    for (int i = KB + 1; i < RPL; ++i) {
+        if ((i - KB) & 1) fmacc(s0, conj_(x[i]), a[i]); else fmacc(s1, conj_(x[i]), a[i]);
+    }
+    T s = s0 + s1;
+    if (q > kq) fmacc(s, conj_(x[KB]), a[KB]);
+    s = group_sum(s);
+    const T ak = shq(a[KB], kq);
+    const T w = t * (ak + conj_(scal) * s);
+    if (update) {                                       // (the shuffles above are executed by every lane of the warp)
+        const T ws = scal * w;
+#pragma unroll
+        for (int i = KB + 1; i < RPL; ++i) fms(a[i], x[i], ws);
+        if (q > kq) fms(a[KB], x[KB], ws);
+        else if (q == kq) a[KB] = a[KB] - w;
+    }
+}
+
+template <typename T, int NMAX, int KB> struct Small2Block {
+    using C = SmallCfg<T, NMAX>;
+    static constexpr int RPL = C::RPL, QLD = C::QLD, CLD = C::CLD;
+
+    // columns k = 4 KB .. 4 KB + 3 of the pivoted QR
+    static __device__ __forceinline__ void factor(T (&a)[RPL], bool& live, int& mypos, int n, int c, int q, int lane,
+                                                  T* mirror, T* mycol, T* tau_s, T* scal_s, double* keys, double* xn_s,
+                                                  double* d_s, int* jpvt_s, SmallProf& pf) {
+#pragma unroll 1
+        for (int kq = 0; kq < 4; ++kq) {
+            const int k = 4 * KB + kq;
+            if (k >= n) break;
+            const int par = (k & 1) * NMAX;
+            // 1. exact partial norms of this column below / from row k, and the live rows of the column itself
+            {
+                const double mb = abs2_(a[KB]);
+                double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+                for (int i = KB + 1; i < RPL; ++i) {
+                    if ((i - KB) & 1) p0 += abs2_(a[i]); else p1 += abs2_(a[i]);
+                }
+                double pl = p0 + p1;
+                if (q > kq) pl += mb;
+                const double xn2 = group_sum(pl);            // bit-identical in the four lanes
+                const double e = shq(mb, kq);
+                if (q == 0) { keys[par + c] = live ? xn2 + e : -1.0; xn_s[par + c] = xn2; }
+                if (live) store_rows<T, RPL, KB>(mycol, a);
+            }
+            pf.stamp(0);
+            __syncthreads();
+            pf.stamp(1);
+            // 2. pivot: largest key, first index among equals (every warp redundantly)
+            double bv = -2.0;
+            int bi = 0;
+#pragma unroll
+            for (int j = 0; j < C::KPL; ++j) {
+                const double v = keys[par + lane + 32 * j];
+                if (v > bv) { bv = v; bi = lane + 32 * j; }
+            }
+            const int hi = __double2hiint(bv);
+            const unsigned lo = (unsigned)__double2loint(bv);
+            const int m1 = __reduce_max_sync(FULL, hi);
+            const unsigned m2 = __reduce_max_sync(FULL, hi == m1 ? lo : 0u);
+            int pvt = __reduce_min_sync(FULL, (hi == m1 && lo == m2) ? bi : 0x7fffffff);
+            pvt = min(pvt, NMAX - 1);
+#ifdef SLA_SMALL_PROFILE
+            if (pvt == 12345) pf.t += 1;   // (the stamp waits for the pivot)
+#endif
+            pf.stamp(2);
+            // 3. its reflector (LAPACK ?larfg), every thread for itself; x = the caller's rows of the pivot column
+            const double xn2p = xn_s[par + pvt];
+            const T alpha = mirror[(size_t)pvt * CLD + kq * QLD + KB];
+            T x[RPL];
+            load_rows<T, RPL, KB>(x, mirror + (size_t)pvt * CLD + q * QLD);
+            T tau, scal;
+            double beta;
+            if (xn2p == 0.0 && imag_(alpha) == 0.0) {        // H = I
+                tau = mk<T>(0.0); scal = mk<T>(0.0); beta = real_(alpha);
+            } else {
+                beta = -copysign(sqrt(abs2_(alpha) + xn2p), real_(alpha));
+                tau = mk<T>((beta - real_(alpha)) / beta, -imag_(alpha) / beta);
+                scal = mk<T>(1.0) / (alpha - mk<T>(beta));
+            }
+#ifdef SLA_SMALL_PROFILE
+            if (real_(scal) == 12345.678) pf.t += 1;   // (the stamp waits for the scalars)
+#endif
+            pf.stamp(3);
+            apply_reflector<T, RPL, KB>(a, x, q, kq, conj_(tau), scal, live && c != pvt);   // ?laqp2: ?larf with conj(tau)
+#ifdef SLA_SMALL_PROFILE
+            if (real_(a[KB]) == 12345.678) pf.t += 1;
+#endif
+            pf.stamp(4);
+            if (c == pvt) {
+                live = false;
+                mypos = k;
+                if (q == kq) a[KB] = mk<T>(beta);
+                if (q == 0) { tau_s[k] = tau; scal_s[k] = scal; d_s[k] = fabs(beta); jpvt_s[k] = pvt; }
+            }
+        }
+    }
+
+    // H_k for k = 4 KB + 3 .. 4 KB applied to the caller's slice of a column of Q (k <= kstart only)
+    static __device__ __forceinline__ void formq(T (&a)[RPL], int n, int kstart, int q, const T* mirror, const T* tau_s,
+                                                 const T* scal_s, const int* jpvt_s) {
+#pragma unroll 1
+        for (int kq = 3; kq >= 0; --kq) {
+            const int k = 4 * KB + kq;
+            if (k >= n || k > kstart) continue;
+            T x[RPL];
+            load_rows<T, RPL, KB>(x, mirror + (size_t)jpvt_s[k] * CLD + q * QLD);
+            apply_reflector<T, RPL, KB>(a, x, q, kq, tau_s[k], scal_s[k], true);
+        }
+    }
+};
+
+template <typename T, int NMAX, int KB> struct Small2Run {
+    using B = Small2Block<T, NMAX, KB>;
+    template <typename... A> static __device__ __forceinline__ void factor(int n, A&&... args) {
+        if (4 * KB < n) {
+            B::factor(static_cast<A&&>(args)...);
+            if constexpr (KB + 1 < B::RPL) Small2Run<T, NMAX, KB + 1>::factor(n, static_cast<A&&>(args)...);
+        }
+    }
+    template <typename... A> static __device__ __forceinline__ void formq(int n, A&&... args) {
+        if (4 * KB < n) {
+            if constexpr (KB + 1 < B::RPL) Small2Run<T, NMAX, KB + 1>::formq(n, static_cast<A&&>(args)...);
+            B::formq(static_cast<A&&>(args)...);
+        }
+    }
+};
+
+template <typename T, int NMAX>
+__global__ void __launch_bounds__(NMAX * 4) ldr_small2_kernel(LdrArgs<T> p) {
+    using C = SmallCfg<T, NMAX>;
+    constexpr int RPL = C::RPL, QLD = C::QLD, CLD = C::CLD;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* mirror = reinterpret_cast<T*>(smem_raw);
+    T* tau_s = mirror + (size_t)NMAX * CLD;     // [NMAX] by step
+    T* scal_s = tau_s + NMAX;                   // [NMAX] by step
+    double* keys = reinterpret_cast<double*>(scal_s + NMAX);   // [2][NMAX]  squared norm of rows >= k, -1 = retired
+    double* xn_s = keys + 2 * NMAX;             // [2][NMAX]  squared norm of rows > k
+    double* d_s = xn_s + 2 * NMAX;              // [NMAX] |beta| by step
+    int* jpvt_s = reinterpret_cast<int*>(d_s + NMAX);          // [NMAX] column retired at step k
+
+    const int n = p.n, b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int c = tid >> 2, q = tid & 3;
+    const bool col_ok = c < n;
+    T* const mycol = mirror + (size_t)c * CLD + q * QLD;
+
+    T a[RPL];
+    {
+        const T* src = p.Ain ? p.Ain + (long long)b * p.strideAin + (long long)c * p.ldain
+                             : p.L + (long long)b * p.strideL + (long long)c * p.ldl;
+        double ss = 0.0;
+        int nz = 0;
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+            const int r = 4 * i + q;
+            a[i] = (col_ok && r < n) ? src[r] : mk<T>(0.0);
+            ss += abs2_(a[i]);
+            nz |= !is_zero(a[i]);
+        }
+        ss = group_sum(ss);
+        nz |= __shfl_xor_sync(FULL, nz, 1);
+        nz |= __shfl_xor_sync(FULL, nz, 2);
+        if (q == 0 && col_ok && ldr_norm2_out_of_range(ss, nz != 0)) ldr_raise_range(p.info, b);
+    }
+    bool live = col_ok;
+    int mypos = -1;   // step at which this column was retired
+
+    SmallProf pf;
+    pf.start();
+    Small2Run<T, NMAX, 0>::factor(n, a, live, mypos, n, c, q, lane, mirror, mycol, tau_s, scal_s, keys, xn_s, d_s, jpvt_s, pf);
+    __syncthreads();   // the scalars of the last step
+    pf.stamp(5);
+
+    // ---------------------------------------------------------------- d = |diag R'|, R = D^-1 R' P^T
+    {
+        T* R = p.R + (long long)b * p.strideR + (long long)c * p.ldr;
+        if (col_ok) {
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) {
+                const int r = 4 * i + q;
+                if (r < n) R[r] = (r <= mypos) ? a[i] / d_s[r] : mk<T>(0.0);
+            }
+        }
+        if (tid < n) {
+            p.d[(long long)b * p.stride_d + tid] = d_s[tid];
+            if (p.jpvt_out) p.jpvt_out[(long long)b * n + tid] = jpvt_s[tid] + 1;
+        }
+    }
+
+    pf.stamp(6);
+    // ---------------------------------------------------------------- Q = H_0 ... H_{n-1} I
+    {
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) a[i] = mk<T>((4 * i + q == c) ? 1.0 : 0.0);
+        // H_k e_c = e_c for k > c: the warp starts at its largest column
+        const int kstart = min(n - 1, 8 * (tid >> 5) + 7);
+        Small2Run<T, NMAX, 0>::formq(n, a, n, kstart, q, mirror, tau_s, scal_s, jpvt_s);
+        T* Q = p.L + (long long)b * p.strideL + (long long)c * p.ldl;
+        if (col_ok) {
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) {
+                const int r = 4 * i + q;
+                if (r < n) Q[r] = a[i];
+            }
+        }
+    }
+#ifdef SLA_SMALL_PROFILE
+    pf.stamp(7);
+    if (p.prof && b == 0 && tid == 0)
+        for (int i = 0; i < 8; ++i) p.prof[i] = pf.acc[i];
+#endif
+}
+
 template <typename T, int NMAX> cudaError_t launch_small(const LdrArgs<T>& p, cudaStream_t stream) {
     using C = SmallCfg<T, NMAX>;
     auto kern = ldr_small_kernel<T, NMAX>;
+    if (C::SMEM > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<p.batch, C::THREADS, C::SMEM, stream>>>(p);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+template <typename T, int NMAX> cudaError_t launch_small2(const LdrArgs<T>& p, cudaStream_t stream) {
+    using C = SmallCfg<T, NMAX>;
+    auto kern = ldr_small2_kernel<T, NMAX>;
     if (C::SMEM > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) return e;
@@ -278,6 +561,14 @@ template <typename T> bool ldr_small_supported(int n) { return n >= 1 && n <= 64
 template <typename T> cudaError_t ldr_small_batched(const LdrArgs<T>& p, cudaStream_t stream) {
     if (p.batch <= 0 || p.n <= 0) return cudaSuccess;
     if (!ldr_small_supported<T>(p.n)) return cudaErrorInvalidValue;
+    // version 2 (row block of the column as a compile-time constant) unless SLA_LDR_SMALL=1 asks for version 1; measured on
+    // one B200 (profiles/ldr_small_r2.txt): ldr! of one 64 x 64 matrix 100.4 -> 67.4 us, 2048 of them 1363 -> 556 us,
+    // ComplexF64 166 -> 121 us, C1 step 1.502 -> 1.189 ms
+    static const int version = [] { const char* e = getenv("SLA_LDR_SMALL"); return e ? atoi(e) : 2; }();
+    if (version != 1) {
+        if (p.n <= 32) return launch_small2<T, 32>(p, stream);
+        return launch_small2<T, 64>(p, stream);
+    }
     if (p.n <= 32) return launch_small<T, 32>(p, stream);
     return launch_small<T, 64>(p, stream);
 }
