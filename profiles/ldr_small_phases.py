@@ -21,8 +21,11 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); sla.ldr_(F, dA, ws); e1.record(); torch.cuda.synchronize()
 lib.sla_debug_set_ldr_prof(None)
 p = prof.cpu().numpy()[:8]
-names = ["norms+store", "barrier", "pivot (keys, 3 redux)", "pivot data + sqrt/rcp", "dot+shuffles+update", "(last barrier)",
-         "R extraction", "Q formation+store"]
-print(f"N={n} batch={batch} kernel={sla.last_ldr_algo()} {e0.elapsed_time(e1) * 1e3:.0f} us; cycles of thread 0, CTA 0: total {p.sum()}")
+ver = os.environ.get("SLA_LDR_SMALL", "3")
+names = (["norms+store (next column)", "barrier 1", "own larfg | pivot | raw dot", "barrier 2", "scalars of the pivot, w, update", "(last barrier)",
+          "R extraction", "Q formation+store"] if ver == "3" else
+         ["norms+store", "barrier", "pivot (keys, 3 redux)", "pivot data + sqrt/rcp", "dot+shuffles+update", "(last barrier)",
+          "R extraction", "Q formation+store"])
+print(f"SLA_LDR_SMALL={ver} N={n} batch={batch} kernel={sla.last_ldr_algo()} {e0.elapsed_time(e1) * 1e3:.0f} us; cycles of thread 0, CTA 0: total {p.sum()}")
 for nm, v in zip(names, p):
-    print(f"  {nm:28s} {v:8d}  ({v / n:7.0f} per column)")
+    print(f"  {nm:34s} {v:8d}  ({v / n:7.0f} per column)")

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libsla_b200.so")
-SOURCES = ["sla_gemm.cu", "sla_gemm_sa.cu", "sla_ldr.cu", "sla_ldr_cluster.cu", "sla_ldr_reg.cu", "sla_ldr_blk.cu", "sla_ldr_mc.cu", "sla_ldr_pp.cu", "sla_ldr_small.cu", "sla_orgq.cu", "sla_lu.cu", "sla_ops.cu", "sla_capi.cu", "sla_capi_f32.cu"]
+SOURCES = ["sla_gemm.cu", "sla_gemm_sa.cu", "sla_ldr.cu", "sla_ldr_cluster.cu", "sla_ldr_reg.cu", "sla_ldr_blk.cu", "sla_ldr_mc.cu", "sla_ldr_pp.cu", "sla_ldr_small.cu", "sla_orgq.cu", "sla_lu.cu", "sla_lu_small.cu", "sla_ops.cu", "sla_capi.cu", "sla_capi_f32.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

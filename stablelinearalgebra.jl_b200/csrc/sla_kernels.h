@@ -73,6 +73,9 @@ template <typename T> struct LuArgs {
 };
 template <typename T> cudaError_t lu_batched(const LuArgs<T>& p, cudaStream_t s);
 template <typename T> bool lu_supported(int n);   // the panels of an n x n matrix fit the shared memory of one CTA
+// n <= 64, inverse form: one CTA per matrix, Gauss-Jordan in registers (sla_lu_small.cu)
+template <typename T> bool lu_small_applies(const LuArgs<T>& p);
+template <typename T> cudaError_t lu_small_inverse_batched(const LuArgs<T>& p, cudaStream_t s);
 
 // ---- element-wise / small kernels (sla_ops.cu) ---------------------------------------------
 // dst = rowscale(rs) * op(src) * colscale(cs); src may be shared (stride 0); op in {OP_N, OP_C}

@@ -531,6 +531,7 @@ static int lu_cluster_size(int n, int batch, int invert) {
 
 template <typename T> cudaError_t lu_batched(const LuArgs<T>& p_in, cudaStream_t stream) {
     if (p_in.batch <= 0 || p_in.n <= 0) return cudaSuccess;
+    if (lu_small_applies<T>(p_in)) return lu_small_inverse_batched<T>(p_in, stream);   // n <= 64, inverse: sla_lu_small.cu
     static const bool pipe_off = getenv("SLA_LU_PIPE") && atoi(getenv("SLA_LU_PIPE")) == 0;   // A/B experiments
     LuArgs<T> p = p_in;
     p.pipe = pipe_off ? 0 : 1;

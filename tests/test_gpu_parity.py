@@ -216,6 +216,63 @@ def test_det_inv_lu(S, n, complex_):
         assert relerr(Xi[b], np.linalg.inv(A[b])) < 1e-13 * np.linalg.cond(A[b]) + 1e-12
 
 
+@pytest.mark.parametrize("complex_", [False, True])
+def test_inv_lu_small_kernel(S, complex_):
+    """n <= 64: inv_lu! is one CTA per matrix, Gauss-Jordan with partial pivoting in registers (csrc/sla_lu_small.cu).  Every
+    size class (n <= 32 and n <= 64 instantiations, n not a multiple of 4, n = 1), batches of one and of several hundred
+    matrices, against numpy; exact ties in the pivot search (identity, a permutation, +-1 entries); run-to-run bit identity;
+    and the same inverse as the general kernel (SLA_LU_SMALL=0 is covered by the sizes above 64 of test_det_inv_lu)."""
+    if os.environ.get("SLA_LU_SMALL"):
+        pytest.skip("the small LU kernel is switched through the environment in this process")
+    rng = np.random.default_rng(4242)
+    for n, batch in [(1, 2), (2, 1), (3, 5), (7, 1), (31, 2), (32, 1), (33, 3), (50, 2), (63, 1), (64, 1), (64, 300), (20, 700)]:
+        A = rand_matrix(rng, n, complex_, batch)
+        outs = []
+        for _ in range(2):
+            X = S.to_device(A)
+            ws = S.ldr_workspace(X)
+            logdet, sgn = S.inv_lu_(X, ws)
+            S.check_info(ws)
+            outs.append((S.to_host(X), logdet.cpu().numpy().copy(), sgn.cpu().numpy().copy()))
+        assert all(np.array_equal(x, y) for x, y in zip(outs[0], outs[1]))
+        Xi, ld, sg = outs[0]
+        for b in range(0, batch, max(1, batch // 3)):
+            sref, lref = np.linalg.slogdet(A[b])
+            cond = np.linalg.cond(A[b])
+            assert relerr(Xi[b], np.linalg.inv(A[b])) < 1e-13 * cond + 1e-12
+            assert np.max(np.abs(Xi[b] @ A[b] - np.eye(n))) < 1e-11 * cond + 1e-11
+            assert abs(ld[b] + lref) < 1e-10 * max(1, n) and abs(sg[b] - np.conj(sref)) < 1e-10
+    one = (1.0 + 0j) if complex_ else 1.0
+    perm = rng.permutation(13)
+    P = np.eye(13)[perm]
+    T = np.sign(rng.standard_normal((2, 24, 24))) * one          # +-1 entries: every pivot search has ties
+    for M in (np.eye(13)[None] * one, P[None] * one, 3.0 * P[None] * (1j if complex_ else -1.0), T):
+        X = S.to_device(M)
+        ws = S.ldr_workspace(X)
+        logdet, sgn = S.inv_lu_(X, ws)
+        S.check_info(ws)
+        Xi = S.to_host(X)
+        for b in range(M.shape[0]):
+            sref, lref = np.linalg.slogdet(M[b])
+            assert relerr(Xi[b], np.linalg.inv(M[b])) < 1e-12 * np.linalg.cond(M[b])
+            assert abs(float(logdet[b]) + lref) < 1e-10 and abs(complex(sgn[b]) - np.conj(sref)) < 1e-10
+    assert np.array_equal(S.to_host(S_inv(S, np.eye(13)[None] * one)), np.eye(13)[None] * one)
+    # a zero pivot is reported like the general kernel reports it (1-based column), and only the first failure
+    Z = rand_matrix(rng, 10, complex_, 3)
+    Z[1][:, 4] = 0.0
+    X = S.to_device(Z)
+    ws = S.ldr_workspace(X)
+    S.inv_lu_(X, ws)
+    info = ws.info().cpu().numpy()
+    assert info[0] == 0 and info[2] == 0 and info[1] > 0
+
+
+def S_inv(S, M):
+    X = S.to_device(M)
+    S.inv_lu_(X, S.ldr_workspace(X))
+    return X
+
+
 @pytest.mark.parametrize("n,batch,complex_", [(256, 64, False), (200, 5, False), (130, 70, True), (512, 6, False), (1024, 2, False)])
 def test_inv_lu_cluster_pipeline(S, n, batch, complex_):
     """The cluster form of the LU inverse (2 or 4 CTAs per matrix when the batch leaves SMs free): the peers form L^-1 P
