@@ -16,12 +16,12 @@
 // inverse like src/lu.jl:157.  Ties in |a_rk| go to the smallest row index (LAPACK: smallest current position).
 //
 // Shape: thread (c, q) = (tid / 4, tid % 4) holds rows q, q+4, ... of slot c (NMAX / 4 values).  Per step k:
-//   A. the warp that owns slot k finds the pivot inside the slot's group of 4 lanes (integer compares on |a| bit patterns,
-//      two shuffle rounds), forms 1 / u_kk and the multipliers m_r = a_rk / u_kk, publishes them and p_k, and turns its slot
-//      into the new column of the inverse (-m_r, 1 / u_kk in row p_k);
+//   A. the warp that owns slot k publishes column k as it stands, finds the pivot inside the slot's group of 4 lanes (integer
+//      compares on |a| bit patterns, two shuffle rounds) and publishes p_k and 1 / u_kk -- nothing else: seven of the eight
+//      warps wait for this one;
 //   -- barrier --
-//   B. every other slot:  a_pc = its element in row p_k (one shuffle inside the group),  a_r -= m_r a_pc  for r != p_k,
-//      a_pk = a_pc / u_kk.
+//   B. every other slot:  a_pc = its element in row p_k (one shuffle inside the group),  t = a_pc / u_kk,
+//      a_r -= a_rk t  for r != p_k,  a_pk = t;  slot k turns into the column the inverse gains: -a_rk / u_kk, 1 / u_kk in row p_k.
 #include <stdlib.h>
 
 #include "sla_kernels.h"
@@ -59,6 +59,40 @@ template <typename T, int RPL, int LO, int HI> __device__ __forceinline__ void l
     }
 }
 
+template <typename T, int RPL> __device__ __forceinline__ void ls_load(T (&x)[RPL], const T* __restrict__ src) {
+    if constexpr (is_cplx<T>::value) {
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) x[i] = src[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < RPL; i += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(src + i);
+            x[i] = t.x; x[i + 1] = t.y;
+        }
+    }
+}
+template <typename T, int RPL> __device__ __forceinline__ void ls_store(T* __restrict__ dst, const T (&x)[RPL]) {
+    if constexpr (is_cplx<T>::value) {
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) dst[i] = x[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < RPL; i += 2) *reinterpret_cast<double2*>(dst + i) = make_double2(x[i], x[i + 1]);
+    }
+}
+// 1 / u_kk: MUFU seed + two Newton steps (an ulp or two from the IEEE quotient, without its slow-path call on the chain)
+// inside the range where the seed is valid; IEEE division for zero, tiny, huge and non-finite pivots
+__device__ __forceinline__ double ls_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    const double ax = fabs(x);
+    if (!(ax > 1e-290 && ax < 1e290)) y = 1.0 / x;
+    return y;
+}
+__device__ __forceinline__ cplx ls_rcp(cplx x) { return cplx{1.0, 0.0} / x; }
+
 // |a| as ?getf2 / i?amax compare it, as an integer key: the bit pattern of a non-negative double is monotone; NaN -> -1
 __device__ __forceinline__ long long ls_key(double x) {
     const double v = fabs(x);
@@ -81,7 +115,7 @@ template <typename T, int NMAX>
 __global__ void __launch_bounds__(NMAX * 4) lu_small_inv_kernel(LuArgs<T> p) {
     using C = LuSmallCfg<T, NMAX>;
     constexpr int RPL = C::RPL, QLD = C::QLD;
-    __shared__ __align__(16) T mul_s[2][4 * QLD];    // multipliers of the step, [lane of the group][row / 4]; 0 in row p_k
+    __shared__ __align__(16) T col_s[2][4 * QLD];    // column k at step k, [lane of the group][row / 4]
     __shared__ T rcp_s[2];                           // 1 / u_kk
     __shared__ int piv_s[2];                         // p_k
     __shared__ T pv_s[NMAX];                         // u_kk by step
@@ -114,8 +148,9 @@ __global__ void __launch_bounds__(NMAX * 4) lu_small_inv_kernel(LuArgs<T> p) {
 #pragma unroll 1
     for (int k = 0; k < n; ++k) {
         const int par = k & 1;
-        // ---- A. the warp of slot k: pivot, reciprocal, multipliers, the slot's new column
+        // ---- A. the warp of slot k: column k, pivot, reciprocal
         if ((k >> 3) == warp) {
+            if (c == k) ls_store<T, RPL>(&col_s[par][q * QLD], a);   // column k as it stands: everybody's multipliers come from it
             long long bk0 = -3, bk1 = -3;
             int br0 = 0, br1 = 0;
             T bv0 = mk<T>(0.0), bv1 = mk<T>(0.0);
@@ -135,32 +170,33 @@ __global__ void __launch_bounds__(NMAX * 4) lu_small_inv_kernel(LuArgs<T> p) {
             }
             const int pr = br0;                      // pivot row (an unused row always exists: keys of unused rows are >= -1)
             const T pv = bv0;
-            const T rc = mk<T>(1.0) / pv;
+            const T rc = ls_rcp(pv);
             if (c == k) {
                 const bool singular = is_zero(pv) || !ls_finite(pv);
                 if (singular && bad == 0) bad = k + 1;
-                T* mrow = &mul_s[par][q * QLD];
-#pragma unroll
-                for (int i = 0; i < RPL; ++i) {
-                    const bool is_p = (4 * i + q == pr);
-                    const T m = is_p ? mk<T>(0.0) : a[i] * rc;
-                    mrow[i] = m;
-                    a[i] = is_p ? rc : -m;
-                }
                 if (q == 0) { rcp_s[par] = rc; piv_s[par] = pr; pv_s[k] = pv; prow_s[k] = pr; kofr_s[pr] = k; }
             }
         }
         __syncthreads();
-        // ---- B. every other slot
+        // ---- B. every slot
         const int pr = piv_s[par];
+        const T rc = rcp_s[par];
         const int ip = pr >> 2, qp = pr & 3;
         const T apc = ls_shq(ls_get<T, RPL, 0, RPL>(a, ip), qp);
-        if (c != k && slot_ok) {
-            const T rc = rcp_s[par];
-            const T* mrow = &mul_s[par][q * QLD];
+        if (slot_ok) {
+            if (c != k) {
+                const T t = apc * rc;                // a_pc / u_kk: the new element in row p_k
+                T col[RPL];
+                ls_load<T, RPL>(col, &col_s[par][q * QLD]);
 #pragma unroll
-            for (int i = 0; i < RPL; ++i) fms(a[i], mrow[i], apc);
-            if (q == qp) ls_set<T, RPL, 0, RPL>(a, ip, apc * rc);
+                for (int i = 0; i < RPL; ++i) fms(a[i], col[i], t);
+                if (q == qp) ls_set<T, RPL, 0, RPL>(a, ip, t);
+            } else {                                 // the column the inverse gains: -a_rk / u_kk, 1 / u_kk in row p_k
+                const T nrc = -rc;
+#pragma unroll
+                for (int i = 0; i < RPL; ++i) a[i] = a[i] * nrc;
+                if (q == qp) ls_set<T, RPL, 0, RPL>(a, ip, rc);
+            }
         }
         if (q == qp) usedm |= 1u << ip;
     }
