@@ -16,9 +16,9 @@
 // inverse like src/lu.jl:157.  Ties in |a_rk| go to the smallest row index (LAPACK: smallest current position).
 //
 // Shape: thread (c, q) = (tid / 4, tid % 4) holds rows q, q+4, ... of slot c (NMAX / 4 values).  Per step k:
-//   A. the warp that owns slot k publishes column k as it stands, finds the pivot inside the slot's group of 4 lanes (integer
-//      compares on |a| bit patterns, two shuffle rounds) and publishes p_k and 1 / u_kk -- nothing else: seven of the eight
-//      warps wait for this one;
+//   A. the warp that owns slot k publishes column k as it stands, finds the pivot over it with all 32 lanes (integer compares
+//      on |a| bit patterns, three `redux` rounds) and publishes p_k and 1 / u_kk -- nothing else: seven of the eight warps wait
+//      for this one;
 //   -- barrier --
 //   B. every other slot:  a_pc = its element in row p_k (one shuffle inside the group),  t = a_pc / u_kk,
 //      a_r -= a_rk t  for r != p_k,  a_pk = t;  slot k turns into the column the inverse gains: -a_rk / u_kk, 1 / u_kk in row p_k.
@@ -139,10 +139,10 @@ __global__ void __launch_bounds__(NMAX * 4) lu_small_inv_kernel(LuArgs<T> p) {
             a[i] = (slot_ok && r < n) ? src[r] : mk<T>(0.0);
         }
     }
-    unsigned usedm = 0;                              // bit i: row 4 i + q has been a pivot row (rows >= n count as used)
+    unsigned used2 = 0;                              // bit h: row lane + 32 h has been a pivot row (rows >= n count as used)
 #pragma unroll
-    for (int i = 0; i < RPL; ++i)
-        if (4 * i + q >= n) usedm |= 1u << i;
+    for (int h = 0; h < NMAX / 32; ++h)
+        if ((tid & 31) + 32 * h >= n) used2 |= 1u << h;
     int bad = 0;                                     // first step with a zero / non-finite pivot, 1-based (group of slot k)
 
 #pragma unroll 1
@@ -151,25 +151,26 @@ __global__ void __launch_bounds__(NMAX * 4) lu_small_inv_kernel(LuArgs<T> p) {
         // ---- A. the warp of slot k: column k, pivot, reciprocal
         if ((k >> 3) == warp) {
             if (c == k) ls_store<T, RPL>(&col_s[par][q * QLD], a);   // column k as it stands: everybody's multipliers come from it
-            long long bk0 = -3, bk1 = -3;
-            int br0 = 0, br1 = 0;
-            T bv0 = mk<T>(0.0), bv1 = mk<T>(0.0);
+            // The search runs over the published column with all 32 lanes (rows lane and lane + 32), not inside the four lanes
+            // that hold it: the seven other warps wait for this one (ncu: 62 % of the kernel's stall samples were their
+            // barrier waits when the group searched its 16 registers per lane serially).
+            __syncwarp();
+            const int lane = tid & 31;
+            long long bk = -3;
+            int br = 0;
 #pragma unroll
-            for (int i = 0; i < RPL; ++i) {
-                const long long key = ((usedm >> i) & 1u) ? -2LL : ls_key(a[i]);
-                if (i & 1) { if (key > bk1) { bk1 = key; br1 = 4 * i + q; bv1 = a[i]; } }
-                else { if (key > bk0) { bk0 = key; br0 = 4 * i + q; bv0 = a[i]; } }
+            for (int h = 0; h < NMAX / 32; ++h) {
+                const int r = lane + 32 * h;
+                const long long key = ((used2 >> h) & 1u) ? -2LL : ls_key(col_s[par][(r & 3) * QLD + (r >> 2)]);
+                if (key > bk) { bk = key; br = r; }
             }
-            if (bk1 > bk0 || (bk1 == bk0 && br1 < br0)) { bk0 = bk1; br0 = br1; bv0 = bv1; }
-#pragma unroll
-            for (int m = 1; m <= 2; m <<= 1) {
-                const long long ok = ls_shx(bk0, m);
-                const int orow = __shfl_xor_sync(LS_FULL, br0, m);
-                const T ov = ls_shx(bv0, m);
-                if (ok > bk0 || (ok == bk0 && orow < br0)) { bk0 = ok; br0 = orow; bv0 = ov; }
-            }
-            const int pr = br0;                      // pivot row (an unused row always exists: keys of unused rows are >= -1)
-            const T pv = bv0;
+            const int hi = (int)(bk >> 32);
+            const unsigned lo = (unsigned)(bk & 0xffffffffLL);
+            const int m1 = __reduce_max_sync(LS_FULL, hi);
+            const unsigned m2 = __reduce_max_sync(LS_FULL, hi == m1 ? lo : 0u);
+            int pr = __reduce_min_sync(LS_FULL, (hi == m1 && lo == m2) ? br : 0x7fffffff);   // first maximal row
+            pr = min(pr, NMAX - 1);                  // (an unused row always exists: keys of unused rows are >= -1)
+            const T pv = col_s[par][(pr & 3) * QLD + (pr >> 2)];
             const T rc = ls_rcp(pv);
             if (c == k) {
                 const bool singular = is_zero(pv) || !ls_finite(pv);
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(NMAX * 4) lu_small_inv_kernel(LuArgs<T> p) {
                 if (q == qp) ls_set<T, RPL, 0, RPL>(a, ip, rc);
             }
         }
-        if (q == qp) usedm |= 1u << ip;
+        if ((pr & 31) == (tid & 31)) used2 |= 1u << (pr >> 5);
     }
     __syncthreads();
 
