@@ -28,6 +28,7 @@ struct sla_handle_s {
     cudaStream_t side_more[3] = {};   // further side streams: consecutive sub-chunks of group products go round-robin over them
     cudaEvent_t ev_start = nullptr;
     cudaEvent_t ev_chunk[64] = {};
+    cudaEvent_t ev_r0 = nullptr, ev_r1 = nullptr;   // small problems: the R product of a stabilisation on its own stream
     int n_events = 0;
     // fused chain driver: the ~100-350 launches of one call captured once into a CUDA graph and replayed while the
     // arguments stay the same (small problems are bound by launch latency, and a multi-GPU host issues 8 x 200 launches
@@ -659,6 +660,8 @@ static int ensure_side_stream(sla_handle_t h) {
     for (int i = 0; i < 3; ++i) CK(cudaStreamCreateWithPriority(&h->side_more[i], cudaStreamNonBlocking, lo));
     CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
     for (int i = 0; i < 64; ++i) CK(cudaEventCreateWithFlags(&h->ev_chunk[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_r0, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_r1, cudaEventDisableTiming));
     h->n_events = 64;
     return 0;
 }
@@ -694,6 +697,14 @@ int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const
     // measured on the C2 step (gpurun_out/r2_sides.log): 1 stream x 2 groups 31.69 ms, 2 streams x 1 group 31.43, 2 x 2 32.27,
     // 3 x 1 32.11, 4 x 1 32.62 -- small low-priority launches leave the SMs to the chain's cluster kernels sooner
     if (overlap) CKI(ensure_side_stream(h));
+    // Small problems (C1: one 64 x 64 chain) are bound by the length of the launch chain, not by SM-time: the product R0 R
+    // of a stabilisation is needed only by the NEXT R product and by the final inverse, so it leaves the chain for a stream
+    // of its own (joined before the next ldr! overwrites R0, and at the end).  Measured without effect on the SM-time-bound
+    // C2 step (profiles/launches_r2g_C2_step_summary.txt), hence the size gate; SLA_RFORK=0/1 overrides it.
+    static const int rfork_env = getenv("SLA_RFORK") ? atoi(getenv("SLA_RFORK")) : -1;
+    const bool rfork = overlap && (rfork_env >= 0 ? rfork_env != 0 : (long long)n * n * batch <= 64LL * 64 * 8);
+    cudaStream_t rstream = rfork ? h->side_more[2] : s;
+    bool r_pending = false;
     for (int g0 = 0; g0 < ng; g0 += gc) {
         const int gcur = (ng - g0 < gc) ? (ng - g0) : gc;
         const int SUB = SUB0 > (gcur + 63) / 64 ? SUB0 : (gcur + 63) / 64;   // at most 64 sub-chunks (events) per pass
@@ -760,11 +771,23 @@ int greens_chain_impl(sla_handle_t h, int n, int batch, int L, int n_stab, const
                 continue;
             }
             CKI(c.gemm(c.w.M, OP_N, Bg, nn, OP_N, XL, nn, nullptr, SCALE_NONE, Xd, SCALE_MUL));
+            if (r_pending) CK(cudaStreamWaitEvent(s, h->ev_r1, 0));   // the previous R product has consumed R0
             CKI(c.ldr(XL, Xd, c.w.Mp, c.w.M, nn));
-            CKI(c.gemm(XR2, OP_N, c.w.Mp, nn, OP_N, XR, nn));
+            if (rfork) {
+                CK(cudaEventRecord(h->ev_r0, s));
+                CK(cudaStreamWaitEvent(rstream, h->ev_r0, 0));
+                Ctx<T> cr = c;
+                cr.s = rstream;
+                CKI(cr.gemm(XR2, OP_N, c.w.Mp, nn, OP_N, XR, nn));
+                CK(cudaEventRecord(h->ev_r1, rstream));
+                r_pending = true;
+            } else {
+                CKI(c.gemm(XR2, OP_N, c.w.Mp, nn, OP_N, XR, nn));
+            }
             T* t = XR; XR = XR2; XR2 = t;
         }
     }
+    if (r_pending) CK(cudaStreamWaitEvent(s, h->ev_r1, 0));
     if (inverse == SLA_INV_IPA) {
         CKI(inv_IpA_impl<T>(h, n, batch, G, FL, Fd, FR, logdet, sign, cw.ws));
         if (Lout) CKI(c.copy(Lout, FL));
@@ -979,6 +1002,8 @@ int sla_destroy(sla_handle_t handle) {
         for (int i = 0; i < 3; ++i) if (handle->side_more[i]) cudaStreamDestroy(handle->side_more[i]);
         if (handle->ev_start) cudaEventDestroy(handle->ev_start);
         for (int i = 0; i < handle->n_events; ++i) cudaEventDestroy(handle->ev_chunk[i]);
+        if (handle->ev_r0) cudaEventDestroy(handle->ev_r0);
+        if (handle->ev_r1) cudaEventDestroy(handle->ev_r1);
     }
     delete handle;
     return 0;
