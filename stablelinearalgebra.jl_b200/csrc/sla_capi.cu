@@ -202,9 +202,9 @@ template <typename T> struct Ctx {
             else if (batch <= 66) cs_mc = 2;
             if (forced == 6) cs_mc = (mc_forced_cs == 2 || mc_forced_cs == 4 || mc_forced_cs == 8) ? mc_forced_cs : 4;
         }
-        // n <= 64: one CTA per matrix with the matrix in registers and one barrier per column (sla_ldr_small.cu) -- the
-        // cluster kernels' per-column machinery costs ~3000 cycles per column at this size, the small kernel's chain is a
-        // few hundred; SLA_LDR_SMALL=0 switches it off, SLA_LDR_ALGO=tiny forces it
+        // n <= 64: one CTA per matrix with the matrix in registers (sla_ldr_small.cu) -- the cluster kernels' per-column
+        // machinery costs ~3000 cycles per column at this size, the small kernel's chain ~1300 (114 -> 61 us for one 64 x 64
+        // matrix); SLA_LDR_SMALL=0 switches it off (1, 2: its earlier versions), SLA_LDR_ALGO=tiny forces it
         static const bool small_on = !(getenv("SLA_LDR_SMALL") && atoi(getenv("SLA_LDR_SMALL")) == 0);
         int algo;
         if (forced == 7 || (forced == 0 && panel_mode)) { if (!ldr_pp_supported<T>(n)) return SLA_ENOTIMPL; algo = SLA_LDR_ALGO_PANEL; }
