@@ -1,5 +1,12 @@
 """Cycles per phase of the small-matrix LDR kernel, version 2 (thread 0 of CTA 0; library built with -DSLA_SMALL_PROFILE and
-selected through SLA_B200_LIB): python profiles/ldr_small_phases.py [N] [batch]"""
+selected through SLA_B200_LIB): python profiles/ldr_small_phases.py [N] [batch]
+
+Build of the profiling library (from stablelinearalgebra.jl_b200/csrc, after the normal build has filled build/):
+  nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
+       -DSLA_SMALL_PROFILE -c sla_ldr_small.cu -o /tmp/small_prof.o
+  nvcc -shared -o abl/libsla_b200_smallprof.so $(ls build/*.o | grep -v sla_ldr_small.o) /tmp/small_prof.o \
+       -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -cudart static
+  SLA_B200_LIB=$PWD/abl/libsla_b200_smallprof.so SLA_LDR_SMALL=3 python ../../profiles/ldr_small_phases.py 64 1"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
